@@ -1,0 +1,194 @@
+/*
+ * mwd_b200.h -- C ABI of the B200-native EM hot path for MultimodalWordDiscovery's
+ * HMM / HMM-DNN word discoverers.
+ *
+ * The reference is pure Python/NumPy and has no FFI; its "operator boundary" is the method
+ * surface of its word-discoverer classes.  Each entry point below replaces the per-caption Python
+ * loop behind one (group of) reference method(s); the file:line it stands in for is cited.  A
+ * maintainer of the reference binds these with ctypes; the package
+ * `multimodalworddiscovery_b200` does exactly that.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `*_d` / `const double*` etc. argument marked [dev] is a
+ *     DEVICE pointer on the current CUDA device, [host] is a host pointer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and the call returns without synchronising unless stated otherwise;
+ *   - return value 0 = success, non-zero = failure; `mwd_last_error()` gives the message
+ *     (thread-local); nothing is thrown across the boundary;
+ *   - all probabilities / counts are IEEE float64 in the raw probability domain, exactly as in
+ *     the reference (EPS = 1e-50 floors included); region features are float32 or float64.
+ *
+ * Corpus layout ("packed pairs").  Pairs (caption, image) are sorted by (n regions, T phones) and
+ * stored CSR-style:
+ *     region_off[N+1] (int32)  -> rows of feats[R][D]   (row-major, D contiguous)
+ *     phone_off [N+1] (int32)  -> entries of phones[Ttot] (int32 phone ids in [0,P))
+ * A "bucket" is a contiguous range of pairs with the same n: pairs [bucket_lo[b], bucket_lo[b+1])
+ * have n == bucket_n[b].
+ *
+ * Parameter layout
+ *     init  [(MWD_NMAX+1)][MWD_NMAX]            init[m][i]      (reference: self.init[m][i])
+ *     trans [(MWD_NMAX+1)][MWD_NMAX*MWD_NMAX]   trans[m][i*m+j] (reference: self.trans[m][i][j])
+ *     obsT  [P][K]                              obsT[p][k] = self.obs[k][p]  (transposed)
+ *     W     [K][D+1]   (linear)   |   mus [K][D]  (gaussian)
+ */
+#ifndef MWD_B200_H
+#define MWD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MWD_NMAX 16          /* max regions (HMM states) per image                       */
+#define MWD_KMAX 128         /* max concepts (nWords)                                     */
+#define MWD_EPS 1e-50        /* hmm_dnn/image_phone_hmm_word_discoverer.py:11             */
+#define MWD_INIT_STRIDE MWD_NMAX
+#define MWD_TRANS_STRIDE (MWD_NMAX * MWD_NMAX)
+
+const char* mwd_last_error(void);
+int mwd_version(void);
+
+/* device / launch geometry the host side needs to size workspaces ------------------------- */
+typedef struct {
+  int32_t sm_count;          /* multiprocessors of the current device                      */
+  int32_t estep_grid;        /* persistent grid of mwd_ik_estep (= rows of the partial tables) */
+  int32_t grad_splits;       /* row-splits of mwd_ik_posterior_grad                          */
+} mwd_geometry;
+int mwd_get_geometry(mwd_geometry* out);
+
+/* packed corpus + parameters + workspaces of the (region i, concept k)-state model -------- */
+typedef struct {
+  /* corpus */
+  int64_t n_pairs;           /* N (this rank's shard)                                       */
+  int64_t n_regions;         /* R = region_off[N]                                           */
+  int64_t n_phones_total;    /* Ttot = phone_off[N]                                         */
+  int32_t feat_dim;          /* D                                                           */
+  int32_t feat_is_f64;       /* 0: feats are float32, 1: float64                            */
+  int32_t n_concepts;        /* K  (<= MWD_KMAX)                                            */
+  int32_t n_phone_types;     /* P                                                           */
+  int32_t t_max;             /* longest caption in the shard                                */
+  int32_t n_buckets;
+  const int32_t* bucket_n;   /* [host] n of each bucket                                     */
+  const int64_t* bucket_lo;  /* [host] n_buckets+1 pair offsets                             */
+  const int32_t* bucket_tmax;/* [host] longest caption of each bucket                       */
+  const int32_t* region_off; /* [dev]                                                       */
+  const int32_t* phone_off;  /* [dev]                                                       */
+  const void*    feats;      /* [dev] R x D                                                 */
+  const int32_t* phones;     /* [dev] Ttot                                                  */
+  /* parameters */
+  const double* init;        /* [dev] see layout above                                      */
+  const double* trans;       /* [dev]                                                       */
+  const double* obsT;        /* [dev] P x K                                                 */
+  /* per-region work/outputs */
+  double* pz;                /* [dev] R x K  image posterior p(z|v)                         */
+  double* concept_counts;    /* [dev] R x K  reference: self.conceptCounts                  */
+  /* per-pair outputs */
+  double* pair_ll;           /* [dev] N      log(max(sum alpha_{T-1}, EPS))                 */
+  double* concept_counts_a;  /* [dev] Ttot x K or NULL  reference: self.conceptCountsA      */
+  /* count partials (one row per persistent CTA) and scratch */
+  double* part_phone;        /* [dev] estep_grid x P x K                                    */
+  double* part_init;         /* [dev] estep_grid x (MWD_NMAX+1) x MWD_NMAX                  */
+  double* part_trans;        /* [dev] estep_grid x (MWD_NMAX+1) x MWD_NMAX*MWD_NMAX         */
+  double* scratch;           /* [dev] checkpoint scratch, scratch_bytes long                */
+  int64_t scratch_bytes;
+} mwd_ik_problem;
+
+/* bytes of `scratch` mwd_ik_estep needs for this problem (depends on t_max, bucket_n, K) */
+int64_t mwd_ik_scratch_bytes(const mwd_ik_problem* p);
+
+/* softmaxLayer -- image_phone_hmm_word_discoverer.py:533-541:
+ *   pz[r][k] = softmax_k( feats[r] . W[k][0:D] + W[k][D] )                                  */
+int mwd_posterior_linear(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
+                         const double* W, int n_concepts, double* pz, void* stream);
+
+/* softmaxLayer -- image_phone_gaussian_hmm_word_discoverer.py:501-510:
+ *   pz[r][k] = softmax_k( -||feats[r] - mus[k]||^2 / width )
+ * w_scratch [dev] K x (D+1) receives the expanded weights [2 mu/width , -||mu||^2/width]      */
+int mwd_posterior_gaussian(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
+                           const double* mus, double width, int n_concepts, double* w_scratch,
+                           double* pz, void* stream);
+
+/* forward + backward + updateInitialCounts + updateTransitionCounts + updateStateCounts +
+ * computeAvgLogLikelihood -- image_phone_hmm_word_discoverer.py:276-433, 523-531, and the
+ * phoneCounts / conceptCountsA accumulation of trainUsingEM :230-235.
+ * Reads p->pz; writes pair_ll, (concept_counts_a), and ACCUMULATES into part_phone / part_init /
+ * part_trans (the caller zeroes them at the start of an EM iteration).  part_init/part_trans hold one table
+ * per n: layout [estep_grid][MWD_NMAX+1][...] -- see mwd_ik_partial_sizes.                   */
+int mwd_ik_estep(const mwd_ik_problem* p, void* stream);
+
+/* computeAvgLogLikelihood alone -- :523-531: forward sweep only, writes p->pair_ll.          */
+int mwd_ik_loglik(const mwd_ik_problem* p, void* stream);
+
+typedef struct {
+  int64_t phone_elems;       /* estep_grid * P * K                                          */
+  int64_t init_elems;        /* estep_grid * (MWD_NMAX+1) * MWD_NMAX                         */
+  int64_t trans_elems;       /* estep_grid * (MWD_NMAX+1) * MWD_NMAX * MWD_NMAX              */
+} mwd_partial_sizes;
+int mwd_ik_partial_sizes(int n_concepts, int n_phone_types, mwd_partial_sizes* out);
+
+/* updateConceptCounts -- image_phone_hmm_word_discoverer.py:443-465.  Reads p->pz, writes
+ * p->concept_counts.                                                                        */
+int mwd_ik_concept_counts(const mwd_ik_problem* p, void* stream);
+
+/* Deterministic second-level reduction of the per-CTA partials (fixed order, no atomics):
+ *   counts = [ phoneC (P x K, transposed) | initC ((NMAX+1) x NMAX) | transC ((NMAX+1) x NMAX^2) | sum LL ]
+ * `counts` [dev] has mwd_ik_counts_len(K,P) doubles; this is the buffer that is all-reduced
+ * across GPUs before the M-step.                                                            */
+int64_t mwd_ik_counts_len(int n_concepts, int n_phone_types);
+int mwd_ik_reduce_counts(const mwd_ik_problem* p, double* counts, void* stream);
+
+/* Gradient of the image-posterior parameters -- updateSoftmaxWeight,
+ * image_phone_hmm_word_discoverer.py:475-488 (linear) / gaussian :488-499:
+ *   grad[k][d] = sum_r (concept_counts - pz)[r][k] * [feats[r], 1][d]     (K x (D+1), UNscaled)
+ * grad_partials [dev] : grad_splits x K x (D+1);  grad [dev] : K x (D+1).                    */
+int mwd_ik_posterior_grad(const mwd_ik_problem* p, double* grad_partials, double* grad,
+                          void* stream);
+
+/* M-step of trainUsingEM -- image_phone_hmm_word_discoverer.py:238-258 (gaussian :238-264).
+ * Consumes the (globally reduced) `counts` and `grad`, updates init / trans / obsT and W or mus
+ * in place.  lens[n_lens] [host] are the distinct n of the WHOLE corpus (reference: self.lenProb
+ * keys); toeplitz = (n_lens >= 6) pooling of :399-413 is applied here (it is linear, so it
+ * commutes with the sums over t and over pairs).  n_pairs_global is len(self.vCorpus).       */
+typedef struct {
+  int32_t gaussian;          /* 0 linear (W), 1 gaussian (mus)                              */
+  int32_t n_concepts, n_phone_types, feat_dim;
+  int32_t n_lens;
+  const int32_t* lens;       /* [host]                                                      */
+  int32_t toeplitz;
+  int64_t n_pairs_global;
+  double lr, momentum, width;
+  const double* counts;      /* [dev]                                                       */
+  const double* grad;        /* [dev] K x (D+1)                                             */
+  double* init;              /* [dev] in/out                                                */
+  double* trans;             /* [dev] in/out                                                */
+  double* obsT;              /* [dev] out                                                   */
+  double* posterior_param;   /* [dev] in/out  W (K x (D+1)) or mus (K x D)                  */
+} mwd_ik_mstep_args;
+int mwd_ik_mstep(const mwd_ik_mstep_args* a, void* stream);
+
+/* align + cluster + argmax(conceptCountsA) of printAlignment --
+ * image_phone_hmm_word_discoverer.py:543-597, 620-648.  Reads p->pz.
+ *   alignment        [dev] Ttot   int32  Viterbi region index per phone (bit-exact tie rules)
+ *   align_probs      [dev] sum_p T_p*n_p doubles or NULL  (offset of pair p = ap_off[p])
+ *   ap_off           [dev] N+1 int64 (required iff align_probs != NULL)
+ *   image_concepts   [dev] R      int32  cluster() argmax
+ *   floor_norm: 1 = gaussian class's floored alignProbs normaliser (gaussian :583)           */
+int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int32_t* alignment, double* align_probs,
+                  const int64_t* ap_off, int32_t* image_concepts, void* stream);
+
+/* argmax_k rows[t][k] (first index on ties, NaN-aware like np.argmax) -- printAlignment :628 */
+int mwd_argmax_rows(const double* rows, int64_t n_rows, int n_cols, int32_t* out, void* stream);
+
+/* Dense forward / backward of ONE pair -- forward :276-304 / backward :314-335.
+ * pz_pair [dev] n x K, phones_pair [dev] T; out [dev] T x n x K.                            */
+int mwd_ik_forward_dense(const double* pz_pair, const int32_t* phones_pair, int T, int n, int K,
+                         const double* init, const double* trans, const double* obsT,
+                         double* out, void* stream);
+int mwd_ik_backward_dense(const double* pz_pair, const int32_t* phones_pair, int T, int n, int K,
+                          const double* trans, const double* obsT, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MWD_B200_H */

@@ -1,0 +1,110 @@
+"""ctypes binding of ``libmwd_b200.so`` (C ABI declared in ``include/mwd_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, loading raises and every product code
+path that needs a kernel fails with it.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmwd_b200.so')
+
+NMAX = 16
+KMAX = 128
+INIT_STRIDE = NMAX
+TRANS_STRIDE = NMAX * NMAX
+EPS = 1e-50
+
+
+class MwdError(RuntimeError):
+    pass
+
+
+class Geometry(C.Structure):
+    _fields_ = [('sm_count', C.c_int32), ('estep_grid', C.c_int32), ('grad_splits', C.c_int32)]
+
+
+class IkProblem(C.Structure):
+    _fields_ = [
+        ('n_pairs', C.c_int64), ('n_regions', C.c_int64), ('n_phones_total', C.c_int64),
+        ('feat_dim', C.c_int32), ('feat_is_f64', C.c_int32), ('n_concepts', C.c_int32),
+        ('n_phone_types', C.c_int32), ('t_max', C.c_int32), ('n_buckets', C.c_int32),
+        ('bucket_n', C.c_void_p), ('bucket_lo', C.c_void_p), ('bucket_tmax', C.c_void_p),
+        ('region_off', C.c_void_p), ('phone_off', C.c_void_p), ('feats', C.c_void_p),
+        ('phones', C.c_void_p),
+        ('init', C.c_void_p), ('trans', C.c_void_p), ('obsT', C.c_void_p),
+        ('pz', C.c_void_p), ('concept_counts', C.c_void_p),
+        ('pair_ll', C.c_void_p), ('concept_counts_a', C.c_void_p),
+        ('part_phone', C.c_void_p), ('part_init', C.c_void_p), ('part_trans', C.c_void_p),
+        ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64),
+    ]
+
+
+class PartialSizes(C.Structure):
+    _fields_ = [('phone_elems', C.c_int64), ('init_elems', C.c_int64), ('trans_elems', C.c_int64)]
+
+
+class IkMstepArgs(C.Structure):
+    _fields_ = [
+        ('gaussian', C.c_int32), ('n_concepts', C.c_int32), ('n_phone_types', C.c_int32),
+        ('feat_dim', C.c_int32), ('n_lens', C.c_int32), ('lens', C.c_void_p),
+        ('toeplitz', C.c_int32), ('n_pairs_global', C.c_int64),
+        ('lr', C.c_double), ('momentum', C.c_double), ('width', C.c_double),
+        ('counts', C.c_void_p), ('grad', C.c_void_p), ('init', C.c_void_p), ('trans', C.c_void_p),
+        ('obsT', C.c_void_p), ('posterior_param', C.c_void_p),
+    ]
+
+
+# every symbol include/mwd_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+SYMBOLS = {
+    'mwd_last_error': (C.c_char_p, []),
+    'mwd_version': (_i, []),
+    'mwd_get_geometry': (_i, [C.POINTER(Geometry)]),
+    'mwd_ik_scratch_bytes': (_i64, [C.POINTER(IkProblem)]),
+    'mwd_posterior_linear': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp, _vp]),
+    'mwd_posterior_gaussian': (_i, [_vp, _i, _i64, _i, _vp, _d, _i, _vp, _vp, _vp]),
+    'mwd_ik_estep': (_i, [C.POINTER(IkProblem), _vp]),
+    'mwd_ik_loglik': (_i, [C.POINTER(IkProblem), _vp]),
+    'mwd_ik_partial_sizes': (_i, [_i, _i, C.POINTER(PartialSizes)]),
+    'mwd_ik_concept_counts': (_i, [C.POINTER(IkProblem), _vp]),
+    'mwd_ik_counts_len': (_i64, [_i, _i]),
+    'mwd_ik_reduce_counts': (_i, [C.POINTER(IkProblem), _vp, _vp]),
+    'mwd_ik_posterior_grad': (_i, [C.POINTER(IkProblem), _vp, _vp, _vp]),
+    'mwd_ik_mstep': (_i, [C.POINTER(IkMstepArgs), _vp]),
+    'mwd_ik_decode': (_i, [C.POINTER(IkProblem), _i, _vp, _vp, _vp, _vp, _vp]),
+    'mwd_argmax_rows': (_i, [_vp, _i64, _i, _vp, _vp]),
+    'mwd_ik_forward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'mwd_ik_backward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise MwdError (never fall back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MwdError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                       'or `make -C multimodalworddiscovery_b200/csrc` (there is no CPU fallback)'
+                       % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MwdError('mwd_b200: %s' % load().mwd_last_error().decode('utf-8', 'replace'))
+
+
+def geometry():
+    g = Geometry()
+    check(load().mwd_get_geometry(C.byref(g)))
+    return g

@@ -1,0 +1,272 @@
+"""Device state and the one-EM-iteration driver of the (region i, concept k)-state model.
+
+PyTorch is plumbing only (device memory, streams, torch.distributed); every computation is a
+kernel of libmwd_b200.so called through the C ABI of include/mwd_b200.h.  There is no CPU
+fallback: without a CUDA device or without the built library, construction raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import IkMstepArgs, IkProblem, MwdError, NMAX, PartialSizes
+from .corpus import dense_to_tables, tables_to_dense
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class IKEngine(object):
+    """Holds one rank's packed shard, the model parameters and all workspaces in HBM."""
+
+    def __init__(self, packed, n_concepts, n_phone_types, gaussian=False, device=None,
+                 keep_concept_counts_a=True, process_group=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise MwdError('no CUDA device: the mwd_b200 engine has no CPU fallback')
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.pk = packed
+        self.K, self.P = int(n_concepts), int(n_phone_types)
+        if not (1 <= self.K <= _lib.KMAX):
+            raise ValueError('n_words=%d outside [1,%d]' % (self.K, _lib.KMAX))
+        self.gaussian = bool(gaussian)
+        self.D = int(packed.feats.shape[1])
+        self.pg = process_group
+        self.geom = _lib.geometry()
+        dev = self.device
+        f64 = torch.float64
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+
+        # corpus
+        self.region_off = up(packed.region_off)
+        self.phone_off = up(packed.phone_off)
+        self.feats = up(packed.feats)
+        self.phones = up(packed.phones)
+        self.feat_is_f64 = 1 if packed.feats.dtype == np.float64 else 0
+        # host-side bucket descriptors (kept alive for the struct)
+        self._bucket_n = np.ascontiguousarray(packed.bucket_n, dtype=np.int32)
+        self._bucket_lo = np.ascontiguousarray(packed.bucket_lo, dtype=np.int64)
+        self._bucket_tmax = np.ascontiguousarray(packed.bucket_tmax, dtype=np.int32)
+        N, R, Tt = packed.n_pairs, packed.n_regions, packed.n_phones_total
+        # parameters
+        self.init_t = torch.zeros((NMAX + 1, NMAX), dtype=f64, device=dev)
+        self.trans_t = torch.zeros((NMAX + 1, NMAX * NMAX), dtype=f64, device=dev)
+        self.obsT = torch.zeros((self.P, self.K), dtype=f64, device=dev)
+        pcols = self.D if self.gaussian else self.D + 1
+        self.post = torch.zeros((self.K, pcols), dtype=f64, device=dev)
+        self.w_scratch = torch.zeros((self.K, self.D + 1), dtype=f64, device=dev) if self.gaussian else None
+        # per-region / per-pair outputs
+        self.pz = torch.empty((max(R, 1), self.K), dtype=f64, device=dev)
+        self.cC = torch.empty((max(R, 1), self.K), dtype=f64, device=dev)
+        self.pair_ll = torch.zeros((max(N, 1),), dtype=f64, device=dev)
+        self.cA = torch.empty((max(Tt, 1), self.K), dtype=f64, device=dev) if keep_concept_counts_a else None
+        # partial tables + reduced buffer [counts | grad] (the all-reduce unit)
+        ps = PartialSizes()
+        _lib.check(self.lib.mwd_ik_partial_sizes(self.K, self.P, C.byref(ps)))
+        self.part = torch.zeros((ps.phone_elems + ps.init_elems + ps.trans_elems,), dtype=f64, device=dev)
+        self._part_phone = self.part[:ps.phone_elems]
+        self._part_init = self.part[ps.phone_elems:ps.phone_elems + ps.init_elems]
+        self._part_trans = self.part[ps.phone_elems + ps.init_elems:]
+        self.counts_len = int(self.lib.mwd_ik_counts_len(self.K, self.P))
+        self.grad_len = self.K * (self.D + 1)
+        self.reduced = torch.zeros((self.counts_len + self.grad_len,), dtype=f64, device=dev)
+        self.counts = self.reduced[:self.counts_len]
+        self.grad = self.reduced[self.counts_len:]
+        self.grad_partials = torch.empty((self.geom.grad_splits, self.K, self.D + 1), dtype=f64, device=dev)
+        self._lens = np.ascontiguousarray(np.array(packed.lens, dtype=np.int32))
+        self.toeplitz = 1 if len(packed.lens) >= 6 else 0     # :399
+        self.n_pairs_global = int(packed.n_pairs_global)
+        # checkpoint scratch
+        self.scratch = None
+        prob = self._problem()
+        need = int(self.lib.mwd_ik_scratch_bytes(C.byref(prob)))
+        self.scratch = torch.empty((max(need, 8) // 8 + 1,), dtype=f64, device=dev)
+        self.last_counts = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _problem(self, with_cA=True):
+        pk = self.pk
+        p = IkProblem()
+        p.n_pairs, p.n_regions, p.n_phones_total = pk.n_pairs, pk.n_regions, pk.n_phones_total
+        p.feat_dim, p.feat_is_f64 = self.D, self.feat_is_f64
+        p.n_concepts, p.n_phone_types = self.K, self.P
+        p.t_max = pk.t_max
+        p.n_buckets = len(self._bucket_n)
+        p.bucket_n, p.bucket_lo = _np_ptr(self._bucket_n), _np_ptr(self._bucket_lo)
+        p.bucket_tmax = _np_ptr(self._bucket_tmax)
+        p.region_off, p.phone_off = _ptr(self.region_off), _ptr(self.phone_off)
+        p.feats, p.phones = _ptr(self.feats), _ptr(self.phones)
+        p.init, p.trans, p.obsT = _ptr(self.init_t), _ptr(self.trans_t), _ptr(self.obsT)
+        p.pz, p.concept_counts = _ptr(self.pz), _ptr(self.cC)
+        p.pair_ll = _ptr(self.pair_ll)
+        p.concept_counts_a = _ptr(self.cA) if with_cA else C.c_void_p(0)
+        p.part_phone, p.part_init = _ptr(self._part_phone), _ptr(self._part_init)
+        p.part_trans = _ptr(self._part_trans)
+        p.scratch = _ptr(self.scratch)
+        p.scratch_bytes = self.scratch.numel() * 8 if self.scratch is not None else 0
+        return p
+
+    # ------------------------------------------------------------------ parameters
+    def set_params(self, init, trans, obs, posterior_param):
+        """init/trans: reference dicts keyed by n; obs: (K, P); posterior_param: W (K, D+1) or mus (K, D)."""
+        torch = self.torch
+        it, tt = tables_to_dense(init, trans)
+        self.init_t.copy_(torch.from_numpy(it))
+        self.trans_t.copy_(torch.from_numpy(tt))
+        obs = np.asarray(obs, dtype=np.float64)
+        if obs.shape != (self.K, self.P):
+            raise ValueError('obs shape %s != (%d, %d)' % (obs.shape, self.K, self.P))
+        self.obsT.copy_(torch.from_numpy(np.ascontiguousarray(obs.T)))
+        pp = np.ascontiguousarray(np.asarray(posterior_param, dtype=np.float64))
+        if pp.shape != tuple(self.post.shape):
+            raise ValueError('posterior parameter shape %s != %s' % (pp.shape, tuple(self.post.shape)))
+        self.post.copy_(torch.from_numpy(pp))
+
+    def get_params(self):
+        it = self.init_t.cpu().numpy()
+        tt = self.trans_t.cpu().numpy()
+        init, trans = dense_to_tables(it, tt, self.pk.lens)
+        obs = np.ascontiguousarray(self.obsT.cpu().numpy().T)
+        return init, trans, obs, self.post.cpu().numpy().copy()
+
+    # ------------------------------------------------------------------ kernels
+    def posterior(self, width=1.0):
+        """pz = p(z | v) for every region of the shard (softmaxLayer)."""
+        lib, st = self.lib, self._stream()
+        R = self.pk.n_regions
+        if self.gaussian:
+            _lib.check(lib.mwd_posterior_gaussian(_ptr(self.feats), self.feat_is_f64, R, self.D,
+                                                  _ptr(self.post), float(width), self.K,
+                                                  _ptr(self.w_scratch), _ptr(self.pz), st))
+        else:
+            _lib.check(lib.mwd_posterior_linear(_ptr(self.feats), self.feat_is_f64, R, self.D,
+                                                _ptr(self.post), self.K, _ptr(self.pz), st))
+
+    def loglik_sum(self, width=1.0):
+        """Sum over this shard of log(max(p(x|y), EPS)) under the current parameters (device scalar)."""
+        self.posterior(width)
+        prob = self._problem()
+        _lib.check(self.lib.mwd_ik_loglik(C.byref(prob), self._stream()))
+        return self.pair_ll[:self.pk.n_pairs].sum()
+
+    def estep(self, width=1.0, with_cA=True):
+        """E-step over the shard: fills pz, pair_ll, cC, (cA) and the reduced [counts | grad]."""
+        lib, st = self.lib, self._stream()
+        self.part.zero_()
+        self.posterior(width)
+        prob = self._problem(with_cA=with_cA and self.cA is not None)
+        _lib.check(lib.mwd_ik_estep(C.byref(prob), st))
+        _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st))
+        _lib.check(lib.mwd_ik_reduce_counts(C.byref(prob), _ptr(self.counts), st))
+        _lib.check(lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st))
+
+    def allreduce(self):
+        """Sum [counts | grad] over ranks: all_gather + fixed-rank-order sum (bitwise reproducible)."""
+        torch = self.torch
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(self.pg)
+        if world == 1:
+            return
+        gathered = torch.empty((world, self.reduced.numel()), dtype=self.reduced.dtype, device=self.device)
+        dist.all_gather_into_tensor(gathered, self.reduced, group=self.pg)
+        torch.sum(gathered, dim=0, out=self.reduced)
+
+    def mstep(self, lr, momentum, width=1.0):
+        a = IkMstepArgs()
+        a.gaussian = 1 if self.gaussian else 0
+        a.n_concepts, a.n_phone_types, a.feat_dim = self.K, self.P, self.D
+        a.n_lens, a.lens = len(self._lens), _np_ptr(self._lens)
+        a.toeplitz = self.toeplitz
+        a.n_pairs_global = self.n_pairs_global
+        a.lr, a.momentum, a.width = float(lr), float(momentum), float(width)
+        a.counts, a.grad = _ptr(self.counts), _ptr(self.grad)
+        a.init, a.trans, a.obsT = _ptr(self.init_t), _ptr(self.trans_t), _ptr(self.obsT)
+        a.posterior_param = _ptr(self.post)
+        _lib.check(self.lib.mwd_ik_mstep(C.byref(a), self._stream()))
+
+    def em_iteration(self, lr, momentum, width=1.0, with_cA=True):
+        """One epoch body of trainUsingEM.  Returns the device scalar sum of log-likelihoods
+        (over ALL ranks) of the parameters that entered the iteration."""
+        self.estep(width, with_cA)
+        self.allreduce()
+        ll = self.counts[self.counts_len - 1].clone()
+        self.mstep(lr, momentum, width)
+        return ll
+
+    def decode(self, floor_norm=False, want_probs=True, width=1.0):
+        """align + cluster for every pair of the shard under the CURRENT parameters.
+        Returns (alignment int32 (Ttot,), image_concepts int32 (R,), align_probs f64 ragged | None)."""
+        torch = self.torch
+        pk = self.pk
+        self.posterior(width)
+        ali = torch.empty((max(pk.n_phones_total, 1),), dtype=torch.int32, device=self.device)
+        ic = torch.empty((max(pk.n_regions, 1),), dtype=torch.int32, device=self.device)
+        ap = ap_off = None
+        if want_probs:
+            off = pk.ap_offsets()
+            ap_off = torch.from_numpy(off).to(self.device)
+            ap = torch.empty((max(int(off[-1]), 1),), dtype=torch.float64, device=self.device)
+        prob = self._problem()
+        _lib.check(self.lib.mwd_ik_decode(C.byref(prob), 1 if floor_norm else 0, _ptr(ali), _ptr(ap),
+                                          _ptr(ap_off), _ptr(ic), self._stream()))
+        return ali[:pk.n_phones_total], ic[:pk.n_regions], ap
+
+    def concept_alignment(self):
+        """argmax_k conceptCountsA[t][k] for every phone of the shard (printAlignment :628)."""
+        if self.cA is None:
+            raise MwdError('conceptCountsA was not kept (keep_concept_counts_a=False)')
+        torch = self.torch
+        Tt = self.pk.n_phones_total
+        out = torch.empty((max(Tt, 1),), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.mwd_argmax_rows(_ptr(self.cA), Tt, self.K, _ptr(out), self._stream()))
+        return out[:Tt]
+
+    def dense_sweep(self, pz_pair, phones_pair, backward=False):
+        """forward()/backward() of one pair: (T, n, K) tensor under the current parameters."""
+        torch = self.torch
+        pz_d = torch.from_numpy(np.ascontiguousarray(pz_pair, dtype=np.float64)).to(self.device)
+        ph_d = torch.from_numpy(np.ascontiguousarray(phones_pair, dtype=np.int32)).to(self.device)
+        n, K = pz_pair.shape
+        T = len(phones_pair)
+        out = torch.zeros((T, n, K), dtype=torch.float64, device=self.device)
+        if backward:
+            _lib.check(self.lib.mwd_ik_backward_dense(_ptr(pz_d), _ptr(ph_d), T, n, K, _ptr(self.trans_t),
+                                                      _ptr(self.obsT), _ptr(out), self._stream()))
+        else:
+            _lib.check(self.lib.mwd_ik_forward_dense(_ptr(pz_d), _ptr(ph_d), T, n, K, _ptr(self.init_t),
+                                                     _ptr(self.trans_t), _ptr(self.obsT), _ptr(out),
+                                                     self._stream()))
+        return out.cpu().numpy()
+
+    def posterior_rows(self, v, width=1.0):
+        """softmaxLayer(vSen) for an arbitrary (n, D) feature block under the current parameters."""
+        torch = self.torch
+        dt = np.float64 if self.feat_is_f64 else np.float32
+        v_d = torch.from_numpy(np.ascontiguousarray(v, dtype=dt)).to(self.device)
+        out = torch.empty((v.shape[0], self.K), dtype=torch.float64, device=self.device)
+        st = self._stream()
+        if self.gaussian:
+            _lib.check(self.lib.mwd_posterior_gaussian(_ptr(v_d), self.feat_is_f64, v.shape[0], self.D,
+                                                       _ptr(self.post), float(width), self.K,
+                                                       _ptr(self.w_scratch), _ptr(out), st))
+        else:
+            _lib.check(self.lib.mwd_posterior_linear(_ptr(v_d), self.feat_is_f64, v.shape[0], self.D,
+                                                     _ptr(self.post), self.K, _ptr(out), st))
+        return out.cpu().numpy()
