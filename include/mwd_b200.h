@@ -48,6 +48,9 @@ extern "C" {
 
 const char* mwd_last_error(void);
 int mwd_version(void);
+/* sizeof() of the ABI structs as compiled (which: 0 mwd_geometry, 1 mwd_ik_problem,
+ * 2 mwd_partial_sizes, 3 mwd_ik_mstep_args) -- lets a binding verify its struct mirrors.      */
+int mwd_abi_sizeof(int which);
 
 /* device / launch geometry the host side needs to size workspaces ------------------------- */
 typedef struct {
@@ -167,15 +170,18 @@ typedef struct {
 } mwd_ik_mstep_args;
 int mwd_ik_mstep(const mwd_ik_mstep_args* a, void* stream);
 
-/* align + cluster + argmax(conceptCountsA) of printAlignment --
- * image_phone_hmm_word_discoverer.py:543-597, 620-648.  Reads p->pz.
- *   alignment        [dev] Ttot   int32  Viterbi region index per phone (bit-exact tie rules)
+/* align + cluster of printAlignment -- image_phone_hmm_word_discoverer.py:543-597, 620-648.
+ * Reads p->pz.
+ *   alignment        [dev] Ttot   int32  Viterbi region index per phone (bit-exact tie rules);
+ *                                        INPUT instead when given_alignment != 0 (cluster() only)
  *   align_probs      [dev] sum_p T_p*n_p doubles or NULL  (offset of pair p = ap_off[p])
  *   ap_off           [dev] N+1 int64 (required iff align_probs != NULL)
  *   image_concepts   [dev] R      int32  cluster() argmax
+ *   cluster_scores   [dev] R x K doubles or NULL  cluster() scores
  *   floor_norm: 1 = gaussian class's floored alignProbs normaliser (gaussian :583)           */
-int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int32_t* alignment, double* align_probs,
-                  const int64_t* ap_off, int32_t* image_concepts, void* stream);
+int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int given_alignment, int32_t* alignment,
+                  double* align_probs, const int64_t* ap_off, int32_t* image_concepts,
+                  double* cluster_scores, void* stream);
 
 /* argmax_k rows[t][k] (first index on ties, NaN-aware like np.argmax) -- printAlignment :628 */
 int mwd_argmax_rows(const double* rows, int64_t n_rows, int n_cols, int32_t* out, void* stream);

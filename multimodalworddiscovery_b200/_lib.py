@@ -60,6 +60,7 @@ _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 SYMBOLS = {
     'mwd_last_error': (C.c_char_p, []),
     'mwd_version': (_i, []),
+    'mwd_abi_sizeof': (_i, [_i]),
     'mwd_get_geometry': (_i, [C.POINTER(Geometry)]),
     'mwd_ik_scratch_bytes': (_i64, [C.POINTER(IkProblem)]),
     'mwd_posterior_linear': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp, _vp]),
@@ -72,7 +73,7 @@ SYMBOLS = {
     'mwd_ik_reduce_counts': (_i, [C.POINTER(IkProblem), _vp, _vp]),
     'mwd_ik_posterior_grad': (_i, [C.POINTER(IkProblem), _vp, _vp, _vp]),
     'mwd_ik_mstep': (_i, [C.POINTER(IkMstepArgs), _vp]),
-    'mwd_ik_decode': (_i, [C.POINTER(IkProblem), _i, _vp, _vp, _vp, _vp, _vp]),
+    'mwd_ik_decode': (_i, [C.POINTER(IkProblem), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'mwd_argmax_rows': (_i, [_vp, _i64, _i, _vp, _vp]),
     'mwd_ik_forward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'mwd_ik_backward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -95,6 +96,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for which, st in enumerate((Geometry, IkProblem, PartialSizes, IkMstepArgs)):
+        if lib.mwd_abi_sizeof(which) != C.sizeof(st):
+            raise MwdError('ABI mismatch: %s is %d bytes in libmwd_b200.so, %d in the binding'
+                           % (st.__name__, lib.mwd_abi_sizeof(which), C.sizeof(st)))
     _lib = lib
     return lib
 

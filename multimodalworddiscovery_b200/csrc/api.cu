@@ -45,3 +45,13 @@ extern "C" int mwd_get_geometry(mwd_geometry* out) {
   out->grad_splits = mwd::kGradSplits;
   return 0;
 }
+
+extern "C" int mwd_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(mwd_geometry);
+    case 1: return (int)sizeof(mwd_ik_problem);
+    case 2: return (int)sizeof(mwd_partial_sizes);
+    case 3: return (int)sizeof(mwd_ik_mstep_args);
+    default: return -1;
+  }
+}

@@ -27,8 +27,9 @@ struct DecodeArgs {
   double* align_probs;   // may be null
   const int64_t* ap_off;
   int32_t* image_concepts;
+  double* cluster_scores;   // may be null: R x K
   int64_t n_pairs;
-  int K, Tmax, floor_norm;
+  int K, Tmax, floor_norm, given_alignment;
 };
 
 __device__ __forceinline__ bool np_greater(double cand, double best) {
@@ -52,7 +53,6 @@ __global__ void __launch_bounds__(128) ik_decode_kernel(const DecodeArgs a) {
   double* s_sc = s_p + (size_t)a.Tmax * kNMax;      // [2][NMAX]
   int* s_x = reinterpret_cast<int*>(s_sc + 2 * kNMax);     // [Tmax]
   unsigned char* s_bp = reinterpret_cast<unsigned char*>(s_x + a.Tmax);  // [Tmax][NMAX]
-  __shared__ int s_path_last;
 
   for (int e = tid; e < n * K; e += blockDim.x) s_pz[e] = a.pz[r0 * K + e];
   for (int t = tid; t < T; t += blockDim.x) s_x[t] = ph[t];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) ik_decode_kernel(const DecodeArgs a) {
   const double* pi = a.init + (size_t)n * MWD_INIT_STRIDE;
   double* ap = a.align_probs ? a.align_probs + a.ap_off[pair] : nullptr;
 
-  if (tid < 32) {
+  if (tid < 32 && !a.given_alignment) {
     const int j = tid;
     double sc = 0.0;
     if (j < n) {
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128) ik_decode_kernel(const DecodeArgs a) {
     for (int t = 0; t < T; ++t)
       if (a.alignment[p0 + t] == i) sc = __dmul_rn(sc, __ldg(a.obsT + (size_t)s_x[t] * K + k));
     s_cl[e] = sc;
+    if (a.cluster_scores) a.cluster_scores[r0 * K + e] = sc;
   }
   __syncthreads();
   if (tid < n) {
@@ -243,9 +244,9 @@ __global__ void ik_backward_dense_kernel(const double* __restrict__ pz, const in
 
 using namespace mwd;
 
-extern "C" int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int32_t* alignment,
-                             double* align_probs, const int64_t* ap_off, int32_t* image_concepts,
-                             void* stream) {
+extern "C" int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int given_alignment,
+                             int32_t* alignment, double* align_probs, const int64_t* ap_off,
+                             int32_t* image_concepts, double* cluster_scores, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (p->n_pairs <= 0) return 0;
   MWD_REQUIRE(p->n_pairs <= 0x7fffffff, "too many pairs for one launch");
@@ -266,6 +267,8 @@ extern "C" int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int32_t* a
   a.K = p->n_concepts;
   a.Tmax = p->t_max;
   a.floor_norm = floor_norm;
+  a.given_alignment = given_alignment;
+  a.cluster_scores = cluster_scores;
   size_t smem = ((size_t)kNMax * a.K + (size_t)a.Tmax * kNMax + 2 * kNMax) * sizeof(double) +
                 (size_t)a.Tmax * sizeof(int) + (size_t)a.Tmax * kNMax;
   if ((size_t)kNMax * a.K > (size_t)a.Tmax * kNMax)  // cluster scores reuse the p[t][i] area

@@ -164,16 +164,36 @@ class IKEngine(object):
         _lib.check(self.lib.mwd_ik_loglik(C.byref(prob), self._stream()))
         return self.pair_ll[:self.pk.n_pairs].sum()
 
-    def estep(self, width=1.0, with_cA=True):
-        """E-step over the shard: fills pz, pair_ll, cC, (cA) and the reduced [counts | grad]."""
+    def estep(self, width=1.0, with_cA=True, timers=None):
+        """E-step over the shard: fills pz, pair_ll, cC, (cA) and the reduced [counts | grad].
+        ``timers``: optional list that receives (kernel name, start event, end event) triples
+        recorded on the launching stream (bench.py's per-kernel roofline)."""
         lib, st = self.lib, self._stream()
+        torch = self.torch
+
+        def timed(name, fn):
+            if timers is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            timers.append((name, e0, e1))
+
         self.part.zero_()
-        self.posterior(width)
+        timed('posterior', lambda: self.posterior(width))
         prob = self._problem(with_cA=with_cA and self.cA is not None)
-        _lib.check(lib.mwd_ik_estep(C.byref(prob), st))
-        _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st))
-        _lib.check(lib.mwd_ik_reduce_counts(C.byref(prob), _ptr(self.counts), st))
-        _lib.check(lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st))
+        timed('ik_estep', lambda: _lib.check(lib.mwd_ik_estep(C.byref(prob), st)))
+        timed('ik_concept', lambda: _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st)))
+        timed('reduce_counts', lambda: _lib.check(lib.mwd_ik_reduce_counts(C.byref(prob), _ptr(self.counts), st)))
+        timed('posterior_grad', lambda: _lib.check(
+            lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st)))
+
+    def kernel_launches_per_iteration(self):
+        """Kernels of libmwd_b200.so launched by one em_iteration (for bench.py's gpu_launches)."""
+        nb = int(np.count_nonzero(np.diff(self._bucket_lo) > 0))
+        post = 2 if self.gaussian else 1
+        return post + nb + nb + 5 + 2 + 3
 
     def allreduce(self):
         """Sum [counts | grad] over ranks: all_gather + fixed-rank-order sum (bitwise reproducible)."""
@@ -201,10 +221,10 @@ class IKEngine(object):
         a.posterior_param = _ptr(self.post)
         _lib.check(self.lib.mwd_ik_mstep(C.byref(a), self._stream()))
 
-    def em_iteration(self, lr, momentum, width=1.0, with_cA=True):
+    def em_iteration(self, lr, momentum, width=1.0, with_cA=True, timers=None):
         """One epoch body of trainUsingEM.  Returns the device scalar sum of log-likelihoods
         (over ALL ranks) of the parameters that entered the iteration."""
-        self.estep(width, with_cA)
+        self.estep(width, with_cA, timers)
         self.allreduce()
         ll = self.counts[self.counts_len - 1].clone()
         self.mstep(lr, momentum, width)
@@ -224,9 +244,49 @@ class IKEngine(object):
             ap_off = torch.from_numpy(off).to(self.device)
             ap = torch.empty((max(int(off[-1]), 1),), dtype=torch.float64, device=self.device)
         prob = self._problem()
-        _lib.check(self.lib.mwd_ik_decode(C.byref(prob), 1 if floor_norm else 0, _ptr(ali), _ptr(ap),
-                                          _ptr(ap_off), _ptr(ic), self._stream()))
+        _lib.check(self.lib.mwd_ik_decode(C.byref(prob), 1 if floor_norm else 0, 0, _ptr(ali), _ptr(ap),
+                                          _ptr(ap_off), _ptr(ic), C.c_void_p(0), self._stream()))
         return ali[:pk.n_phones_total], ic[:pk.n_regions], ap
+
+    def decode_pair(self, v, x, floor_norm=False, width=1.0, alignment=None):
+        """align()/cluster() of ONE arbitrary pair under the current parameters.
+        Returns (alignment (T,), align_probs (T, n), image_concepts (n,), cluster_scores (n, K))."""
+        torch = self.torch
+        dev = self.device
+        n, T = int(v.shape[0]), int(len(x))
+        if not (1 <= n <= NMAX):
+            raise ValueError('n=%d outside [1,%d]' % (n, NMAX))
+        dt = np.float64 if self.feat_is_f64 else np.float32
+        v_d = torch.from_numpy(np.ascontiguousarray(v, dtype=dt)).to(dev)
+        x_d = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
+        roff = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        poff = torch.tensor([0, T], dtype=torch.int32, device=dev)
+        pz = torch.empty((n, self.K), dtype=torch.float64, device=dev)
+        st = self._stream()
+        if self.gaussian:
+            _lib.check(self.lib.mwd_posterior_gaussian(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
+                                                       float(width), self.K, _ptr(self.w_scratch), _ptr(pz), st))
+        else:
+            _lib.check(self.lib.mwd_posterior_linear(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
+                                                     self.K, _ptr(pz), st))
+        p = IkProblem()
+        p.n_pairs, p.n_regions, p.n_phones_total = 1, n, T
+        p.feat_dim, p.feat_is_f64, p.n_concepts, p.n_phone_types = self.D, self.feat_is_f64, self.K, self.P
+        p.t_max, p.n_buckets = T, 0
+        p.region_off, p.phone_off, p.feats, p.phones = _ptr(roff), _ptr(poff), _ptr(v_d), _ptr(x_d)
+        p.init, p.trans, p.obsT, p.pz = _ptr(self.init_t), _ptr(self.trans_t), _ptr(self.obsT), _ptr(pz)
+        given = alignment is not None
+        if given:
+            ali = torch.from_numpy(np.ascontiguousarray(alignment, dtype=np.int32)).to(dev)
+        else:
+            ali = torch.empty((T,), dtype=torch.int32, device=dev)
+        ap = torch.zeros((T * n,), dtype=torch.float64, device=dev)
+        ap_off = torch.tensor([0, T * n], dtype=torch.int64, device=dev)
+        ic = torch.empty((n,), dtype=torch.int32, device=dev)
+        cs = torch.empty((n, self.K), dtype=torch.float64, device=dev)
+        _lib.check(self.lib.mwd_ik_decode(C.byref(p), 1 if floor_norm else 0, 1 if given else 0, _ptr(ali),
+                                          _ptr(ap), _ptr(ap_off), _ptr(ic), _ptr(cs), st))
+        return (ali.cpu().numpy(), ap.cpu().numpy().reshape(T, n), ic.cpu().numpy(), cs.cpu().numpy())
 
     def concept_alignment(self):
         """argmax_k conceptCountsA[t][k] for every phone of the shard (printAlignment :628)."""

@@ -1,0 +1,446 @@
+"""Shared host-side logic of the two (region i, concept k)-state word discoverers.
+
+Mirrors the public surface of
+  hmm_dnn/image_phone_hmm_word_discoverer.py            (ImagePhoneHMMWordDiscoverer)
+  hmm_dnn/image_phone_gaussian_hmm_word_discoverer.py   (ImagePhoneGaussianHMMWordDiscoverer)
+-- same constructor signatures, method names, public attributes, prints and on-disk formats --
+while every per-caption computation runs as a CUDA kernel behind include/mwd_b200.h.
+No NumPy/CPU fallback exists for the kernels: without the built library or a GPU, the methods
+that compute raise.
+"""
+import json
+import math
+import random
+import time
+from copy import deepcopy
+
+import numpy as np
+
+from .. import _lib
+from ..corpus import pack_pairs
+
+EPS = 1e-50
+
+
+class OneHotCorpus(object):
+    """Lazy stand-in for the reference's ``aCorpus`` (list of one-hot (T, P) float64 arrays,
+    image_phone_hmm_word_discoverer.py:92-97): indexing materialises one sentence."""
+
+    def __init__(self, phone_ids, n_types):
+        self.ids = phone_ids
+        self.n_types = n_types
+
+    def __len__(self):
+        return len(self.ids)
+
+    def _one(self, x):
+        a = np.zeros((len(x), self.n_types))
+        a[np.arange(len(x)), x] = 1.
+        return a
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(x) for x in self.ids[i]]
+        return self._one(self.ids[i])
+
+    def __iter__(self):
+        for x in self.ids:
+            yield self._one(x)
+
+
+def one_hot_to_ids(aSen):
+    """The kernels take phone ids; a reference-style one-hot (T, P) sentence collapses exactly."""
+    a = np.asarray(aSen)
+    if a.ndim == 1:
+        return a.astype(np.int32)
+    ids = np.argmax(a, axis=1)
+    if not (np.all(a[np.arange(len(ids)), ids] == 1.) and np.count_nonzero(a) == len(ids)):
+        raise ValueError('aSen must be one-hot rows (soft phone posteriors are the image_audio classes)')
+    return ids.astype(np.int32)
+
+
+class ImagePhoneHMMBase(object):
+    GAUSSIAN = False
+
+    # ------------------------------------------------------------------ corpus
+    def _read_features(self, imageFeatFile, limit=None):
+        vNpz = np.load(imageFeatFile)
+        keys = sorted(vNpz.keys(), key=lambda x: int(x.split('_')[-1]))       # :53
+        if limit is not None:
+            keys = keys[:limit]
+        return [vNpz[k] for k in keys]
+
+    def _read_captions(self, speechFeatFile, limit=None):
+        """:78-97 -- phone2idx in first-seen order over the WHOLE file; ids instead of one-hots."""
+        self.phone2idx = {}
+        nTypes = 0
+        nPhones = 0
+        strs = []
+        with open(speechFeatFile, 'r') as f:
+            for line in f:
+                aSen = line.strip().split()
+                strs.append(aSen)
+                for phn in aSen:
+                    if phn not in self.phone2idx:
+                        self.phone2idx[phn] = nTypes
+                        nTypes += 1
+                    nPhones += 1
+        self.audioFeatDim = nTypes
+        if limit is not None:
+            strs = strs[:limit]
+        ids = [np.array([self.phone2idx[p] for p in s], dtype=np.int32) for s in strs]
+        return ids, nTypes, nPhones
+
+    def _finish_corpus(self, ids, nTypes, nPhones):
+        self._phones = ids
+        self.aCorpus = OneHotCorpus(ids, nTypes)
+        nImages = 0
+        for ex, vfeat in enumerate(self.vCorpus):
+            nImages += len(vfeat)
+            if vfeat.shape[-1] == 0:                                            # :70-73
+                print('ex: ', ex)
+                print('vfeat empty: ', vfeat.shape)
+                self.vCorpus[ex] = np.zeros((1, self.imageFeatDim))
+        print('----- Corpus Summary -----')
+        print('Number of examples: ', len(self.aCorpus))
+        print('Number of phonetic categories: ', nTypes)
+        print('Number of phones: ', nPhones)
+        print('Number of objects: ', nImages)
+        print("Number of word clusters: ", self.nWords)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _dist(self):
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        return 0, 1
+
+    def _phone_ids(self):
+        a = self.aCorpus
+        if isinstance(a, OneHotCorpus):
+            return a.ids
+        # the user replaced aCorpus with reference-style one-hot arrays
+        return [one_hot_to_ids(s) for s in a]
+
+    def _engine(self):
+        """(Re)build the device engine when the corpus objects changed."""
+        from ..engine import IKEngine
+        token = (id(self.vCorpus), len(self.vCorpus), id(self.aCorpus), len(self.aCorpus), self.nWords,
+                 self.audioFeatDim)
+        if getattr(self, '_eng', None) is None or self._eng_token != token:
+            rank, world = self._dist()
+            dt = np.float64 if self._feature_dtype == 'float64' else np.float32
+            pk = pack_pairs(self.vCorpus, self._phone_ids(), feat_dtype=dt, rank=rank, world=world)
+            self._eng = IKEngine(pk, self.nWords, self.audioFeatDim, gaussian=self.GAUSSIAN,
+                                 device=self._device, keep_concept_counts_a=self._keep_cA)
+            self._eng_token = token
+            self._cA_valid = False
+        return self._eng
+
+    def _posterior_param(self):
+        return self.mus if self.GAUSSIAN else self.W
+
+    def _set_posterior_param(self, v):
+        if self.GAUSSIAN:
+            self.mus = v
+        else:
+            self.W = v
+
+    def _push(self):
+        eng = self._engine()
+        eng.set_params(self.init, self.trans, self.obs, self._posterior_param())
+        return eng
+
+    def _pull(self, eng):
+        init, trans, obs, post = eng.get_params()
+        for m in init:
+            self.init[m] = init[m]
+            self.trans[m] = trans[m]
+        self.obs = obs
+        self._set_posterior_param(post)
+
+    def _width(self):
+        return float(getattr(self, 'width', 1.))
+
+    # ------------------------------------------------------------------ model
+    def computeTranslationLengthProbabilities(self, smoothing=None):
+        """:491-521, including the per-sentence reset of lenProb[len(ts)] (only the key set and
+        the last sentence's entry survive, as in the reference)."""
+        for ts, fs in zip(self.vCorpus, self._phone_ids()):
+            self.lenProb[len(ts)] = {}
+            if len(fs) not in self.lenProb[len(ts)].keys():
+                self.lenProb[len(ts)][len(fs)] = 1
+            else:
+                self.lenProb[len(ts)][len(fs)] += 1
+        if smoothing == 'laplace':
+            tLenMax = max(list(self.lenProb.keys()))
+            fLenMax = max([max(list(f.keys())) for f in list(self.lenProb.values())])
+            for tLen in range(tLenMax):
+                for fLen in range(fLenMax):
+                    if tLen not in self.lenProb:
+                        self.lenProb[tLen] = {}
+                        self.lenProb[tLen][fLen] = 1.
+                    elif fLen not in self.lenProb[tLen]:
+                        self.lenProb[tLen][fLen] = 1.
+                    else:
+                        self.lenProb[tLen][fLen] += 1.
+        for tl in self.lenProb.keys():
+            totCount = sum(self.lenProb[tl].values())
+            for fl in self.lenProb[tl].keys():
+                self.lenProb[tl][fl] = self.lenProb[tl][fl] / totCount
+
+    def _load_init_trans_files(self, create_missing):
+        if self.initProbFile:
+            with open(self.initProbFile) as f:
+                for line in f:
+                    m, s, prob = line.split()
+                    if create_missing and int(m) not in self.init:               # gaussian :117-118
+                        self.init[int(m)] = np.zeros((int(m),))
+                    self.init[int(m)][int(s)] = float(prob)
+        if self.transProbFile:
+            with open(self.transProbFile) as f:
+                for line in f:
+                    m, cur_s, next_s, prob = line.split()
+                    if create_missing and int(m) not in self.trans:              # gaussian :126-127
+                        self.trans[int(m)] = np.zeros((int(m), int(m)))
+                    self.trans[int(m)][int(cur_s)][int(next_s)] = float(prob)
+
+    # ------------------------------------------------------------------ EM
+    def trainUsingEM(self, numIterations=20, writeModel=False, warmStart=False, convergenceEpsilon=0.01,
+                     printStatus=True, debug=False):
+        """:198-266.  The E-step (forward/backward, expected counts, concept posteriors), the
+        count reduction and the M-step all run on the GPU; the per-epoch log-likelihood the
+        reference computes in a separate pass (:216) is produced by the same forward sweep."""
+        if not warmStart:
+            self.initializeModel()
+        if writeModel:
+            self.printModel('initial_model.txt')
+        eng = self._push()
+        maxLikelihood = -np.inf
+        likelihoods = np.zeros((numIterations,))
+        N = len(self.vCorpus)
+        for epoch in range(numIterations):
+            begin_time = time.time()
+            width = self._width()
+            if printStatus and writeModel:
+                # the reference decides about writing BEFORE the E-step, from a separate LL pass
+                likelihood = float(self._allreduce_scalar(eng.loglik_sum(width))) / N
+                if likelihood > maxLikelihood:
+                    self._pull(eng)
+                    self.printModel(self.modelName + '_iter=' + str(epoch) + '.txt')
+                    # reference quirk: conceptCountsA was just reset to zeros (:213), so the
+                    # intermediate dumps carry concept_alignment == 0 everywhere
+                    self.printAlignment(self.modelName + '_iter=' + str(epoch) + '_alignment', debug=False,
+                                        _zero_concept_alignment=True)
+                    maxLikelihood = likelihood
+            ll = eng.em_iteration(self.lr, self.momentum, width)
+            self._cA_valid = True
+            if printStatus:
+                likelihood = float(ll) / N
+                likelihoods[epoch] = likelihood
+                print('Epoch', epoch, 'Average Log Likelihood:', likelihood)
+            if (epoch + 1) % 10 == 0:
+                self.lr /= 10
+            if printStatus:
+                eng.torch.cuda.synchronize(eng.device)
+                print('Epoch %d takes %.2f s to finish' % (epoch, time.time() - begin_time))
+        self._pull(eng)
+        self._conceptCounts_cache = None
+        self._conceptCountsA_cache = None
+        np.save(self.modelName + '_likelihoods.npy', likelihoods)
+
+    def _allreduce_scalar(self, t):
+        rank, world = self._dist()
+        if world > 1:
+            import torch.distributed as dist
+            t = t.clone()
+            dist.all_reduce(t)
+        return t
+
+    def computeAvgLogLikelihood(self):
+        """:523-531"""
+        eng = self._push()
+        return float(self._allreduce_scalar(eng.loglik_sum(self._width()))) / len(self.vCorpus)
+
+    # per-pair outputs of the last E-step, reference layout (lists in corpus order)
+    def _gather_rows(self, dev_rows, off):
+        eng = self._eng
+        rows = dev_rows.cpu().numpy()
+        rank, world = self._dist()
+        local = [(int(ex), rows[off[s]:off[s + 1]]) for s, ex in enumerate(eng.pk.order)]
+        if world > 1:
+            import torch.distributed as dist
+            allp = [None] * world
+            dist.all_gather_object(allp, local)
+            local = [x for part in allp for x in part]
+        out = [None] * len(self.vCorpus)
+        for ex, r in local:
+            out[ex] = r
+        return out
+
+    @property
+    def conceptCounts(self):
+        if getattr(self, '_conceptCounts_cache', None) is None:
+            if getattr(self, '_eng', None) is None or not getattr(self, '_cA_valid', False):
+                raise AttributeError("'%s' object has no attribute 'conceptCounts'" % type(self).__name__)
+            self._conceptCounts_cache = self._gather_rows(self._eng.cC, self._eng.pk.region_off)
+        return self._conceptCounts_cache
+
+    @conceptCounts.setter
+    def conceptCounts(self, v):
+        self._conceptCounts_cache = v
+
+    @property
+    def conceptCountsA(self):
+        if getattr(self, '_conceptCountsA_cache', None) is None:
+            if getattr(self, '_eng', None) is None or not getattr(self, '_cA_valid', False):
+                raise AttributeError("'%s' object has no attribute 'conceptCountsA'" % type(self).__name__)
+            if self._eng.cA is None:
+                raise _lib.MwdError('conceptCountsA was not kept: set modelConfigs["keep_concept_counts_a"]=True')
+            self._conceptCountsA_cache = self._gather_rows(self._eng.cA, self._eng.pk.phone_off)
+        return self._conceptCountsA_cache
+
+    @conceptCountsA.setter
+    def conceptCountsA(self, v):
+        self._conceptCountsA_cache = v
+
+    # ------------------------------------------------------------------ single-pair API
+    def softmaxLayer(self, vSen, debug=False):
+        """:533-541 / gaussian :501-510"""
+        return self._push().posterior_rows(np.asarray(vSen), self._width())
+
+    def forward(self, vSen, aSen, debug=False):
+        """:276-304 -> (T, n, K)"""
+        eng = self._push()
+        pz = eng.posterior_rows(np.asarray(vSen), self._width())
+        return eng.dense_sweep(pz, one_hot_to_ids(aSen), backward=False)
+
+    def backward(self, vSen, aSen, debug=False):
+        """:314-335 -> (T, n, K)"""
+        eng = self._push()
+        pz = eng.posterior_rows(np.asarray(vSen), self._width())
+        return eng.dense_sweep(pz, one_hot_to_ids(aSen), backward=True)
+
+    def align(self, aSen, vSen, unkProb=10e-12, debug=False):
+        """:543-584 -> (bestPath list[int], alignProbs list[list[float]])"""
+        eng = self._push()
+        ali, ap, _, _ = eng.decode_pair(np.asarray(vSen), one_hot_to_ids(aSen), floor_norm=self.GAUSSIAN,
+                                        width=self._width())
+        return [int(a) for a in ali], ap.tolist()
+
+    def cluster(self, aSen, vSen, alignment):
+        """:586-597 -> (argmax list[int], scores list[list[float]])"""
+        eng = self._push()
+        _, _, ic, cs = eng.decode_pair(np.asarray(vSen), one_hot_to_ids(aSen), floor_norm=self.GAUSSIAN,
+                                       width=self._width(), alignment=np.asarray(alignment))
+        return [int(c) for c in ic], cs.tolist()
+
+    # ------------------------------------------------------------------ I/O
+    def printModel(self, fileName):
+        """:599-616 (+ gaussian :629)"""
+        initFile = open(fileName + '_initialprobs.txt', 'w')
+        for nState in sorted(self.lenProb):
+            for i in range(nState):
+                initFile.write('%d\t%d\t%f\n' % (nState, i, self.init[nState][i]))
+        initFile.close()
+        transFile = open(fileName + '_transitionprobs.txt', 'w')
+        for nState in sorted(self.lenProb):
+            for i in range(nState):
+                for j in range(nState):
+                    transFile.write('%d\t%d\t%d\t%f\n' % (nState, i, j, self.trans[nState][i][j]))
+        transFile.close()
+        np.save(fileName + '_observationprobs.npy', self.obs)
+        with open(fileName + '_phone2idx.json', 'w') as f:
+            json.dump(self.phone2idx, f)
+        if self.GAUSSIAN:
+            np.save(fileName + '_visualanchors.npy', self.mus)
+
+    def _decode_all(self, zero_concept_alignment=False):
+        """Batched align + cluster + argmax(conceptCountsA) for the whole corpus, corpus order."""
+        eng = self._push()
+        ali, ic, ap = eng.decode(floor_norm=self.GAUSSIAN, want_probs=True, width=self._width())
+        pk = eng.pk
+        alis = self._gather_rows(ali, pk.phone_off)
+        ics = self._gather_rows(ic, pk.region_off)
+        aps = self._gather_rows(ap, pk.ap_offsets())
+        if zero_concept_alignment:
+            cas = [np.zeros(len(a), dtype=np.int64) for a in alis]
+        else:
+            # AttributeError before any trainUsingEM, as in the reference (:628)
+            if not getattr(self, '_cA_valid', False):
+                raise AttributeError("'%s' object has no attribute 'conceptCountsA'" % type(self).__name__)
+            if getattr(self, '_conceptCountsA_cache', None) is not None:
+                cas = [np.argmax(c, axis=1) for c in self._conceptCountsA_cache]
+            else:
+                cas = self._gather_rows(eng.concept_alignment(), pk.phone_off)
+        return alis, ics, aps, cas
+
+    def printAlignment(self, filePrefix, isPhoneme=True, debug=False, _zero_concept_alignment=False):
+        """:620-648 (gaussian adds 'concept_probs', :651)"""
+        alis, ics, aps, cas = self._decode_all(_zero_concept_alignment)
+        rank, _ = self._dist()
+        if rank != 0:
+            return
+        f = open(filePrefix + '.txt', 'w')
+        aligns = []
+        for i in range(len(self.vCorpus)):
+            n = len(ics[i])
+            align_info = {
+                'index': i,
+                'image_concepts': [int(c) for c in ics[i]],
+                'concept_alignment': [int(c) for c in cas[i]],
+                'alignment': [int(a) for a in alis[i]],
+                'align_probs': np.asarray(aps[i]).reshape(-1, n).tolist(),
+                'is_phoneme': isPhoneme
+            }
+            if self.GAUSSIAN:
+                align_info['concept_probs'] = np.asarray(self.conceptCounts[i]).tolist()
+            aligns.append(align_info)
+            for a in alis[i]:
+                f.write('%d ' % a)
+            f.write('\n\n')
+        f.close()
+        with open(filePrefix + '.json', 'w') as f:
+            json.dump(aligns, f, indent=4, sort_keys=True)
+
+    # ------------------------------------------------------------------ simulated annealing
+    def simulatedAnnealing(self, numIterations=100, T0=0.5, stepScale=5., debug=False):
+        """:159-196 (gaussian :156-193): same control flow, the EM inside runs on the GPU."""
+        inner = 5 if self.GAUSSIAN else 20
+        self.trainUsingEM(numIterations=5, warmStart=False, printStatus=True)
+        E0 = -self.computeAvgLogLikelihood()
+        Emin = E0
+        count = 0
+        for epoch in range(numIterations):
+            print('Simulated Annealing Iteration %d' % epoch)
+            begin_time = time.time()
+            init_prev = deepcopy(self.init)
+            trans_prev = deepcopy(self.trans)
+            obs_prev = deepcopy(self.obs)
+            p_prev = deepcopy(self._posterior_param())
+            self._set_posterior_param(self._posterior_param()
+                                      + stepScale * np.random.normal(size=self._posterior_param().shape))
+            self.trainUsingEM(numIterations=inner, warmStart=True, printStatus=False)
+            E1 = -self.computeAvgLogLikelihood()
+            print('Current and previous energy level: ', E1, E0)
+            Tk = T0 / np.log(epoch + 2)
+            if E1 > E0 and random.random() > np.exp(-(E1 - E0) / Tk):
+                self._set_posterior_param(p_prev)
+                self.init = init_prev
+                self.trans = trans_prev
+                self.obs = obs_prev
+            else:
+                if debug:
+                    print('Random jump at temperature %.5f' % Tk)
+                E0 = E1
+                if E1 < Emin:
+                    Emin = E1
+                    count += 1
+                    print('Update %d after %.2f s: current lowest energy level is %.5f'
+                          % (count, time.time() - begin_time, Emin))
+                    self.printModel(self.modelName + '_%d' % count)
+                    self.printAlignment(self.modelName + '_%d_alignment' % count, debug=False)
+                    begin_time = time.time()

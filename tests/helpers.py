@@ -34,3 +34,47 @@ def oracle_params_from_golden(g):
         return orc.initial_params(g['feats_list'], g['K'], g['P'], 'linear', W=g['param0'], **kw)
     return orc.initial_params(g['feats_list'], g['K'], g['P'], 'gaussian', mus=g['param0'],
                               width=g['width'], **kw)
+
+
+def write_ik_files(tmp, g):
+    """Write a golden case in the reference's on-disk formats; returns (caps, feats, cfg, extra)."""
+    import os
+    caps = os.path.join(tmp, 'caps.txt')
+    with open(caps, 'w') as f:
+        for x in g['phones_list']:
+            f.write(' '.join('p%d' % p for p in x) + '\n')
+    feats = os.path.join(tmp, 'feats.npz')
+    np.savez(feats, **{'arr_%d' % i: v for i, v in enumerate(g['feats_list'])})
+    cfg = dict(has_null=False, n_words=g['K'], learning_rate=g['lr'], momentum=g['momentum'],
+               width=g['width'], feature_dtype='float64')
+    extra = {}
+    if 'obs0' in g:
+        np.save(os.path.join(tmp, 'obs.npy'), g['obs0'])
+        extra['obs'] = os.path.join(tmp, 'obs.npy')
+    if g['kind'] == 'linear':
+        np.savez(os.path.join(tmp, 'w.npz'), weight=g['param0'][:, :-1], bias=g['param0'][:, -1])
+        cfg['image_posterior_weights_file'] = os.path.join(tmp, 'w.npz')
+    else:
+        np.save(os.path.join(tmp, 'mus.npy'), g['param0'])
+        cfg['visual_anchor_file'] = os.path.join(tmp, 'mus.npy')
+        if 'obs' in extra:
+            cfg['obs_prob_file'] = extra['obs']
+    return caps, feats, cfg, extra
+
+
+def make_model(tmp, g):
+    import contextlib
+    import io
+    import os
+    caps, feats, cfg, extra = write_ik_files(tmp, g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if g['kind'] == 'linear':
+            from multimodalworddiscovery_b200.hmm_dnn.image_phone_hmm_word_discoverer import \
+                ImagePhoneHMMWordDiscoverer
+            m = ImagePhoneHMMWordDiscoverer(caps, feats, cfg, obsProbFile=extra.get('obs'),
+                                            modelName=os.path.join(tmp, 'm'))
+        else:
+            from multimodalworddiscovery_b200.hmm_dnn.image_phone_gaussian_hmm_word_discoverer import \
+                ImagePhoneGaussianHMMWordDiscoverer
+            m = ImagePhoneGaussianHMMWordDiscoverer(caps, feats, cfg, modelName=os.path.join(tmp, 'm'))
+    return m

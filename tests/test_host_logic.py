@@ -1,0 +1,121 @@
+"""CPU tests of the host-side logic: packing, bucketing, sharding, table layout, the C-ABI
+library's exported symbols, and loud failure without a GPU."""
+import contextlib
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import load_ik, make_model
+from multimodalworddiscovery_b200 import _lib
+from multimodalworddiscovery_b200.corpus import (dense_to_tables, pack_pairs, pack_sorted_arrays,
+                                                 shard_positions, tables_to_dense)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _corpus(rng, N=37, D=4, P=6):
+    feats = [rng.standard_normal((int(rng.integers(1, 8)), D)) for _ in range(N)]
+    phones = [rng.integers(0, P, int(rng.integers(1, 20))) for _ in range(N)]
+    return feats, phones
+
+
+def test_pack_sorted_buckets_and_roundtrip():
+    rng = np.random.default_rng(0)
+    feats, phones = _corpus(rng)
+    pk = pack_pairs(feats, phones, feat_dtype=np.float64)
+    n = np.diff(pk.region_off)
+    T = np.diff(pk.phone_off)
+    assert sorted(pk.order.tolist()) == list(range(len(feats)))
+    assert np.all(np.diff(n) >= 0)
+    for b in range(len(pk.bucket_n)):
+        lo, hi = pk.bucket_lo[b], pk.bucket_lo[b + 1]
+        assert np.all(n[lo:hi] == pk.bucket_n[b])
+        assert np.all(np.diff(T[lo:hi]) >= 0) and T[lo:hi].max() == pk.bucket_tmax[b]
+    for s, ex in enumerate(pk.order):
+        np.testing.assert_array_equal(pk.feats[pk.region_off[s]:pk.region_off[s + 1]], feats[ex])
+        np.testing.assert_array_equal(pk.phones[pk.phone_off[s]:pk.phone_off[s + 1]], phones[ex])
+    assert pk.lens == sorted(set(f.shape[0] for f in feats))
+    pk2 = pack_sorted_arrays(pk.region_off, pk.phone_off, pk.feats, pk.phones)
+    np.testing.assert_array_equal(pk2.bucket_lo, pk.bucket_lo)
+    np.testing.assert_array_equal(pk2.bucket_n, pk.bucket_n)
+    np.testing.assert_array_equal(pk2.bucket_tmax, pk.bucket_tmax)
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_sharding_partitions_and_balances(world):
+    rng = np.random.default_rng(1)
+    feats, phones = _corpus(rng, N=203)
+    seen, costs = [], []
+    for r in range(world):
+        pk = pack_pairs(feats, phones, rank=r, world=world)
+        seen += pk.order.tolist()
+        n = np.diff(pk.region_off).astype(float)
+        T = np.diff(pk.phone_off).astype(float)
+        costs.append(float(np.sum(T * n ** 3)))
+        assert pk.n_pairs_global == 203
+        assert pk.lens == sorted(set(f.shape[0] for f in feats))      # global, not per shard
+    assert sorted(seen) == list(range(203))
+    assert max(costs) / min(costs) < 1.35
+    assert shard_positions(10, 1, 4).tolist() == [1, 5, 9]
+
+
+def test_pack_rejects_bad_pairs():
+    rng = np.random.default_rng(2)
+    feats, phones = _corpus(rng, N=5)
+    with pytest.raises(IndexError):
+        pack_pairs(feats, phones[:4] + [np.array([], dtype=int)])
+    with pytest.raises(ValueError):
+        pack_pairs(feats[:4] + [rng.standard_normal((_lib.NMAX + 1, 4))], phones)
+    with pytest.raises(ValueError):
+        pack_pairs(feats, phones[:4])
+
+
+def test_table_layout_roundtrip():
+    rng = np.random.default_rng(3)
+    init = {m: rng.random(m) for m in (1, 3, 7, 16)}
+    trans = {m: rng.random((m, m)) for m in (1, 3, 7, 16)}
+    it, tt = tables_to_dense(init, trans)
+    assert it.shape == (_lib.NMAX + 1, _lib.NMAX) and tt.shape == (_lib.NMAX + 1, _lib.NMAX ** 2)
+    assert tt[3, 1 * 3 + 2] == trans[3][1, 2]
+    i2, t2 = dense_to_tables(it, tt, [1, 3, 7, 16])
+    for m in init:
+        np.testing.assert_array_equal(i2[m], init[m])
+        np.testing.assert_array_equal(t2[m], trans[m])
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/mwd_b200.h declares."""
+    hdr = open(os.path.join(ROOT, 'include', 'mwd_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(mwd_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.mwd_version() >= 100
+    assert lib.mwd_ik_counts_len(65, 49) == 65 * 49 + 17 * 16 + 17 * 256 + 1
+
+
+def test_struct_layout_matches_header():
+    import ctypes as C
+    lib = _lib.load()
+    for which, st in enumerate((_lib.Geometry, _lib.IkProblem, _lib.PartialSizes, _lib.IkMstepArgs)):
+        assert lib.mwd_abi_sizeof(which) == C.sizeof(st)
+
+
+def test_class_constructs_on_cpu_and_compute_fails_loudly(tmp_path):
+    """Host-side reading/initialisation works anywhere; kernels never silently fall back."""
+    import torch
+    g = load_ik('tiny_linear')
+    m = make_model(str(tmp_path), g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.initializeModel()
+    assert sorted(m.lenProb) == [2] and m.obs.shape == (3, 3) and m.W.shape == (3, 4)
+    np.testing.assert_array_equal(m.aCorpus[1], np.array([[0, 1., 0], [0, 0, 1.]]))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.MwdError):
+            m.computeAvgLogLikelihood()
