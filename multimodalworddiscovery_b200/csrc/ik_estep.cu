@@ -42,27 +42,58 @@ struct EstepArgs {
 };
 
 constexpr int NQ = 5;  // exchanged per-row quantities: floor-sum, g-sum, diag, r, xi-row-sum
+constexpr int BMAX = 8; // max checkpoint interval
 
-template <int KG>
-__global__ void __launch_bounds__(kPairsPerCta * kNMax * kLanesPerRow)
+// phone-count table update for one column k and the PP rows deferred by the previous step.
+// All loads are issued first; equal phone ids are forwarded so the result equals the sequential
+// slot-ordered read-modify-write.
+template <int PP>
+__device__ __forceinline__ void drain_column(double* tab, int K, int k, const int* xs, const double* cA) {
+  double v[PP];
+#pragma unroll
+  for (int s = 0; s < PP; ++s) v[s] = (xs[s] >= 0) ? tab[xs[s] * K + k] : 0.0;
+#pragma unroll
+  for (int s = 0; s < PP; ++s) {
+    if (xs[s] < 0) continue;
+#pragma unroll
+    for (int q = 0; q < s; ++q)
+      if (xs[q] == xs[s]) v[s] = v[q];          // latest earlier slot with the same phone wins
+    v[s] += cA[s * K + k];
+  }
+#pragma unroll
+  for (int s = 0; s < PP; ++s)
+    if (xs[s] >= 0) tab[xs[s] * K + k] = v[s];
+}
+
+// KG = ceil(K/8) exactly: only the last of a lane's KG concepts can fall outside [0,K).
+// NJ = ceil(n/8): xi columns per lane.
+template <int KG, int NJ, int PP, bool TAB>
+__global__ void __launch_bounds__(PP * 8 * 8 * NJ, NJ == 1 ? 2 : 1)
 ik_estep_kernel(const EstepArgs a) {
   constexpr int KS = KG * kLanesPerRow;
-  constexpr int PP = kPairsPerCta;
   const int n = a.n, K = a.K, B = a.B;
   const int tid = threadIdx.x;
   const int l8 = tid & 7;
   const int grp = tid >> 3;
   const int slot = grp / n;
   const int i = grp - slot * n;
-  constexpr int NJ = kNMax / kLanesPerRow;  // xi columns per lane
+  const int TX = a.Tmax;
+  const bool kv_last = (l8 + 8 * (KG - 1)) < K;   // validity of this lane's last concept
 
   extern __shared__ double smem[];
-  double* s_buf = smem;                                   // [PP][B][n][KS]
-  double* s_exch = s_buf + (size_t)PP * B * n * KS;       // [2][PP][NQ][NMAX]
-  double* s_aoff = s_exch + 2 * PP * NQ * kNMax;          // [n][n]
-  double* s_d = s_aoff + kNMax * kNMax;                   // [n]
-  double* s_pi = s_d + kNMax;                             // [n]
-  double* s_cA = s_pi + kNMax;                            // [2][PP][K] deferred phone-count rows
+  // shared-memory map (offsets in doubles)
+  const int o_exch = PP * B * n * KS;                     // [2][PP][NQ][NMAX]
+  const int o_aoff = o_exch + 2 * PP * NQ * kNMax;        // [n][n]
+  const int o_d = o_aoff + kNMax * kNMax;                 // [n]
+  const int o_pi = o_d + kNMax;                           // [n]
+  const int o_cA = o_pi + kNMax;                          // [2][PP][K]
+  const int o_tab = o_cA + 2 * PP * K;                    // [P][K]   (TAB)
+  const int o_x = o_tab + (TAB ? a.P * K : 0);            // ints: [PP][TX]
+  double* s_buf = smem;
+  double* s_exch = smem + o_exch;
+  double* s_aoff = smem + o_aoff;
+  double* s_cA = smem + o_cA;
+  int* s_x = reinterpret_cast<int*>(smem + o_x);
   __shared__ int s_T[PP];
   __shared__ int s_xs[2][PP];                             // phone id of the deferred row, -1 = none
 
@@ -71,17 +102,21 @@ ik_estep_kernel(const EstepArgs a) {
     int r = e / n, c = e - r * n;
     double v = a.trans[e];
     s_aoff[e] = (r == c) ? 0.0 : v;
-    if (r == c) s_d[r] = v;
+    if (r == c) smem[o_d + r] = v;
   }
-  for (int e = tid; e < n; e += blockDim.x) s_pi[e] = a.init[e];
+  for (int e = tid; e < n; e += blockDim.x) smem[o_pi + e] = a.init[e];
+  if (TAB)
+    for (int e = tid; e < a.P * K; e += blockDim.x) smem[o_tab + e] = 0.0;
 
   double* cta_scr = a.scratch + (size_t)blockIdx.x * a.cta_scratch;
-  double* ckpt = cta_scr;                                           // [PP][NC][n][KS]
-  double* hist = cta_scr + (size_t)PP * a.NC * n * KS;              // [PP][Tmax][2][n]
-  double* my_ckpt = ckpt + ((size_t)slot * a.NC * n + i) * KS;      // + c*n*KS + k
-  double* my_hist = hist + (size_t)slot * a.Tmax * 2 * n;           // + (t*2+which)*n + i
-  double* my_buf = s_buf + ((size_t)slot * B * n + i) * KS;         // + tt*n*KS + k
-  double* my_phone = a.part_phone + (size_t)blockIdx.x * a.P * K;
+  double* my_ckpt = cta_scr + ((size_t)slot * a.NC * n + i) * KS + l8;              // + c*n*KS + 8j
+  double* my_hist = cta_scr + (size_t)PP * a.NC * n * KS + (size_t)slot * a.Tmax * 2 * n + i;  // + (t*2+w)*n
+  const int buf_row = (slot * B * n + i) * KS + l8;                                  // + tt*n*KS + 8j
+  const int nKS = n * KS;
+  double* g_phone = a.part_phone + (size_t)blockIdx.x * a.P * K;
+  double* tab = TAB ? (smem + o_tab) : g_phone;
+  const int* my_x = s_x + slot * TX;
+  const double* obsT = a.obsT + l8;
 
   // persistent accumulators
   double init_acc = 0.0;          // lane 0 of each row: sum_t floor-sum_i / total
@@ -92,19 +127,17 @@ ik_estep_kernel(const EstepArgs a) {
   const int64_t npairs = a.hi - a.lo;
   const int64_t nquads = (npairs + PP - 1) / PP;
   __syncthreads();
-  const double d_i = s_d[i];
-  const double pi_i = s_pi[i];
+  const double d_i = smem[o_d + i];
+  const double pi_i = smem[o_pi + i];
 
   for (int64_t quad = blockIdx.x; quad < nquads; quad += gridDim.x) {
     const int64_t pair = a.lo + quad * PP + slot;
     const bool valid = pair < a.hi;
     int T = 0;
-    const int32_t* ph = a.phones;
     int64_t r0 = 0, p0 = 0;
     if (valid) {
       p0 = a.phone_off[pair];
       T = a.phone_off[pair + 1] - (int32_t)p0;
-      ph = a.phones + p0;
       r0 = a.region_off[pair];
     }
     __syncthreads();  // previous quad fully done (exchange + buffers reusable)
@@ -113,27 +146,28 @@ ik_estep_kernel(const EstepArgs a) {
       s_xs[0][slot] = -1;
       s_xs[1][slot] = -1;
     }
+    for (int t = i * kLanesPerRow + l8; t < T; t += n * kLanesPerRow)
+      s_x[slot * TX + t] = a.phones[p0 + t];
     __syncthreads();
     int Tmax = 0;
 #pragma unroll
     for (int s = 0; s < PP; ++s) Tmax = max(Tmax, s_T[s]);
 
     double pz[KG];
+    {
+      const double* prow = a.pz + (r0 + i) * K + l8;
 #pragma unroll
-    for (int j = 0; j < KG; ++j) {
-      int k = l8 + 8 * j;
-      pz[j] = (valid && k < K) ? a.pz[(r0 + i) * K + k] : 0.0;
+      for (int j = 0; j < KG; ++j)
+        pz[j] = (valid && (j < KG - 1 || kv_last)) ? prow[8 * j] : 0.0;
     }
 
     // ------------------------------------------------------------------ forward sweep
     double al[KG];
     {
-      int x = valid ? ph[0] : 0;
-      const double* orow = a.obsT + (size_t)x * K;
+      const double* orow = obsT + (valid ? my_x[0] : 0) * K;
 #pragma unroll
       for (int j = 0; j < KG; ++j) {
-        int k = l8 + 8 * j;
-        double o = (k < K) ? __ldg(orow + k) : 0.0;
+        double o = (j < KG - 1 || kv_last) ? __ldg(orow + 8 * j) : 0.0;
         al[j] = (pi_i * pz[j]) * o;
       }
     }
@@ -141,20 +175,27 @@ ik_estep_kernel(const EstepArgs a) {
       const bool act = t < T;
       const int par = t & 1;
       double s = 0.0;
+      double onext[KG];
       if (act) {
-        if (t % B == 0 && !a.ll_only) {
-          double* dst = my_ckpt + (size_t)(t / B) * n * KS;
+        if (t + 1 < T) {   // next step's emissions: issued before the reduction / barrier
+          const double* orow = obsT + my_x[t + 1] * K;
 #pragma unroll
-          for (int j = 0; j < KG; ++j) __stcg(dst + l8 + 8 * j, al[j]);
+          for (int j = 0; j < KG; ++j) onext[j] = (j < KG - 1 || kv_last) ? __ldg(orow + 8 * j) : 0.0;
+        }
+        if (t % B == 0 && !a.ll_only) {
+          double* dst = my_ckpt + (size_t)(t / B) * nKS;
+#pragma unroll
+          for (int j = 0; j < KG; ++j) __stcg(dst + 8 * j, al[j]);
         }
 #pragma unroll
         for (int j = 0; j < KG; ++j) s += al[j];
       }
       s = row8_sum(s);
-      if (l8 == 0) s_exch[((par * PP + slot) * NQ + 0) * kNMax + i] = s;
+      const int exo = ((par * PP + slot) * NQ) * kNMax;
+      if (l8 == 0) s_exch[exo + i] = s;
       __syncthreads();
       if (act) {
-        const double* ex = s_exch + ((par * PP + slot) * NQ + 0) * kNMax;
+        const double* ex = s_exch + exo;
         if (t == T - 1) {
           if (i == 0 && l8 == 0) {
             double L = 0.0;
@@ -165,17 +206,11 @@ ik_estep_kernel(const EstepArgs a) {
           double c = 0.0;
           for (int j = 0; j < n; ++j) c = fma(s_aoff[j * n + i], ex[j], c);
           if (l8 == 0 && !a.ll_only) {
-            __stcg(my_hist + (size_t)(t * 2 + 0) * n + i, c);
-            __stcg(my_hist + (size_t)(t * 2 + 1) * n + i, s);
+            __stcg(my_hist + (t * 2 + 0) * n, c);
+            __stcg(my_hist + (t * 2 + 1) * n, s);
           }
-          int x = ph[t + 1];
-          const double* orow = a.obsT + (size_t)x * K;
 #pragma unroll
-          for (int j = 0; j < KG; ++j) {
-            int k = l8 + 8 * j;
-            double o = (k < K) ? __ldg(orow + k) : 0.0;
-            al[j] = o * fma(d_i, al[j], c * pz[j]);
-          }
+          for (int j = 0; j < KG; ++j) al[j] = onext[j] * fma(d_i, al[j], c * pz[j]);
         }
       }
     }
@@ -193,7 +228,8 @@ ik_estep_kernel(const EstepArgs a) {
     for (int jj = 0; jj < NJ; ++jj) { r_next[jj] = 0.0; x_hold[jj] = 0.0; }
     bool pend = false;
     double zrow = 0.0;
-    int step = 0;           // parity counter of exchange buffers (continues from forward)
+    double s_pref = 0.0;    // s_t[i] prefetched one step ahead
+    int step = 0;           // parity counter of the exchange buffers
 
     const int nblk = (Tmax + B - 1) / B;
     for (int c = nblk - 1; c >= 0; --c) {
@@ -201,24 +237,27 @@ ik_estep_kernel(const EstepArgs a) {
       const int len = min(B, Tmax - t0);
       __syncthreads();  // column reads of the previous block are complete
       if (t0 < T) {
-        const double* src = my_ckpt + (size_t)c * n * KS;
+        const double* src = my_ckpt + (size_t)c * nKS;
+        double cb[BMAX];
+#pragma unroll
+        for (int tt = 1; tt < BMAX; ++tt)
+          cb[tt] = (tt < len && t0 + tt < T) ? __ldcg(my_hist + ((t0 + tt - 1) * 2 + 0) * n) : 0.0;
 #pragma unroll
         for (int j = 0; j < KG; ++j) {
-          al[j] = __ldcg(src + l8 + 8 * j);
-          my_buf[l8 + 8 * j] = al[j];
+          al[j] = __ldcg(src + 8 * j);
+          s_buf[buf_row + 8 * j] = al[j];
         }
-        for (int tt = 1; tt < len && t0 + tt < T; ++tt) {
-          const int t = t0 + tt;
-          double cprev = __ldcg(my_hist + (size_t)((t - 1) * 2 + 0) * n + i);
-          int x = ph[t];
-          const double* orow = a.obsT + (size_t)x * K;
-          double* dst = my_buf + (size_t)tt * n * KS;
 #pragma unroll
-          for (int j = 0; j < KG; ++j) {
-            int k = l8 + 8 * j;
-            double o = (k < K) ? __ldg(orow + k) : 0.0;
-            al[j] = o * fma(d_i, al[j], cprev * pz[j]);
-            dst[l8 + 8 * j] = al[j];
+        for (int tt = 1; tt < BMAX; ++tt) {
+          if (tt < len && t0 + tt < T) {
+            const double* orow = obsT + my_x[t0 + tt] * K;
+            double* dst = s_buf + buf_row + tt * nKS;
+#pragma unroll
+            for (int j = 0; j < KG; ++j) {
+              double o = (j < KG - 1 || kv_last) ? __ldg(orow + 8 * j) : 0.0;
+              al[j] = o * fma(d_i, al[j], cb[tt] * pz[j]);
+              dst[8 * j] = al[j];
+            }
           }
         }
       }
@@ -226,28 +265,28 @@ ik_estep_kernel(const EstepArgs a) {
         const int t = t0 + tt;
         const bool act = t < T;
         const int par = step & 1;
-        double sumF = 0.0, sumG = 0.0, dg = 0.0, rr = 0.0, s_cur = 0.0;
+        double sumF = 0.0, sumG = 0.0, dg = 0.0, rr = 0.0;
+        const double s_cur = s_pref;
+        if (t >= 1 && t - 1 < T - 1) s_pref = __ldcg(my_hist + ((t - 1) * 2 + 1) * n);
         int x = 0;
         if (act) {
-          x = ph[t];
+          x = my_x[t];
           const bool last = (t == T - 1);
-          if (!last) s_cur = __ldcg(my_hist + (size_t)(t * 2 + 1) * n + i);
-          const double* orow = a.obsT + (size_t)x * K;
-          double* row = my_buf + (size_t)tt * n * KS;
+          const double* orow = obsT + x * K;
+          double* row = s_buf + buf_row + tt * nKS;
 #pragma unroll
           for (int j = 0; j < KG; ++j) {
-            int k = l8 + 8 * j;
-            const bool kv = k < K;
-            double av = row[l8 + 8 * j];
+            const bool kv = (j < KG - 1) || kv_last;
+            double av = row[8 * j];
             double beta = last ? 1.0 : fma(d_i, bo[j], w);
             dg = fma(av, bo[j], dg);
             double g = av * beta;
             sumG += g;
             sumF += kv ? floor_eps(g) : 0.0;
-            double o = kv ? __ldg(orow + k) : 0.0;
+            double o = kv ? __ldg(orow + 8 * j) : 0.0;
             bo[j] = beta * o;
             rr = fma(bo[j], pz[j], rr);
-            row[l8 + 8 * j] = g;
+            row[8 * j] = g;
           }
           dg *= d_i;
         }
@@ -257,8 +296,9 @@ ik_estep_kernel(const EstepArgs a) {
         rr = row8_sum(rr);
         double zr = row8_sum(zrow);
         zrow = 0.0;
+        const int exo = ((par * PP + slot) * NQ) * kNMax;
         if (l8 == 0) {
-          double* ex = s_exch + ((par * PP + slot) * NQ) * kNMax + i;
+          double* ex = s_exch + exo + i;
           ex[0 * kNMax] = sumF;
           ex[1 * kNMax] = sumG;
           ex[2 * kNMax] = dg;
@@ -269,16 +309,11 @@ ik_estep_kernel(const EstepArgs a) {
         // drain the phone-count rows deferred by the previous step: thread k owns column k of
         // the per-CTA table for every slot, so the read-modify-writes never race and their
         // order (t descending, slot ascending) is fixed.
-        for (int k = tid; k < K; k += blockDim.x) {
-#pragma unroll
-          for (int s = 0; s < PP; ++s) {
-            int xs = s_xs[par ^ 1][s];
-            if (xs >= 0) my_phone[(size_t)xs * K + k] += s_cA[((par ^ 1) * PP + s) * K + k];
-          }
-        }
+        for (int k = tid; k < K; k += blockDim.x)
+          drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
         if (i == 0 && l8 == 0) s_xs[par][slot] = act ? x : -1;
         if (act) {
-          const double* ex = s_exch + ((par * PP + slot) * NQ) * kNMax;
+          const double* ex = s_exch + exo;
           double Ft = 0.0, Gt = 0.0, Zt = 0.0, wn = 0.0;
           for (int j = 0; j < n; ++j) {
             Ft += ex[0 * kNMax + j];
@@ -286,10 +321,11 @@ ik_estep_kernel(const EstepArgs a) {
             Zt += ex[4 * kNMax + j];
             wn = fma(s_aoff[i * n + j], ex[3 * kNMax + j], wn);
           }
-          if (l8 == 0) init_acc += sumF / Ft;                    // :355
+          if (l8 == 0) init_acc += sumF * __drcp_rn(Ft);         // :355
           if (pend) {                                            // normalise xi_{t+1}  (:396)
+            const double iz = __drcp_rn(Zt);
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) trans_acc[jj] += x_hold[jj] / Zt;
+            for (int jj = 0; jj < NJ; ++jj) trans_acc[jj] = fma(x_hold[jj], iz, trans_acc[jj]);
             pend = false;
           }
           if (t < T - 1) {                                       // xi_t  (:388-389)
@@ -314,39 +350,36 @@ ik_estep_kernel(const EstepArgs a) {
           }
           w = wn;
           // conceptCountsA[t][k] = sum_i gamma_t[i][k]; phoneCounts[k][x_t] += ...  (:430,:233,:235)
-          const double norm = floor_eps(Gt);
-          const double* col = s_buf + ((size_t)slot * B + tt) * n * KS;
+          const double inorm = __drcp_rn(floor_eps(Gt));
+          const double* col = s_buf + (slot * B + tt) * nKS;
           double* crow = s_cA + (par * PP + slot) * K;
           for (int k = i * kLanesPerRow + l8; k < K; k += n * kLanesPerRow) {
             double v = 0.0;
             for (int ii = 0; ii < n; ++ii) v += col[ii * KS + k];
-            v /= norm;
+            v *= inorm;
             crow[k] = v;
             if (a.cA_out) a.cA_out[(p0 + t) * K + k] = v;
           }
         }
       }
     }
-    // flush the last pending xi normaliser (xi_0)
+    // flush the last pending xi normaliser (xi_0) and the last deferred phone-count rows
     {
       const int par = step & 1;
       double zr = row8_sum(zrow);
       zrow = 0.0;
-      if (l8 == 0) s_exch[((par * PP + slot) * NQ + 4) * kNMax + i] = zr;
+      const int exo = ((par * PP + slot) * NQ + 4) * kNMax;
+      if (l8 == 0) s_exch[exo + i] = zr;
       __syncthreads();
-      for (int k = tid; k < K; k += blockDim.x) {
-#pragma unroll
-        for (int s = 0; s < PP; ++s) {
-          int xs = s_xs[par ^ 1][s];
-          if (xs >= 0) my_phone[(size_t)xs * K + k] += s_cA[((par ^ 1) * PP + s) * K + k];
-        }
-      }
+      for (int k = tid; k < K; k += blockDim.x)
+        drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
       if (pend) {
-        const double* ex = s_exch + ((par * PP + slot) * NQ + 4) * kNMax;
+        const double* ex = s_exch + exo;
         double Zt = 0.0;
         for (int j = 0; j < n; ++j) Zt += ex[j];
+        const double iz = __drcp_rn(Zt);
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) trans_acc[jj] += x_hold[jj] / Zt;
+        for (int jj = 0; jj < NJ; ++jj) trans_acc[jj] = fma(x_hold[jj], iz, trans_acc[jj]);
         pend = false;
       }
     }
@@ -355,6 +388,8 @@ ik_estep_kernel(const EstepArgs a) {
   if (a.ll_only) return;
   // ---------------------------------------------------------------- per-CTA partial tables
   __syncthreads();
+  if (TAB)
+    for (int e = tid; e < a.P * K; e += blockDim.x) g_phone[e] += smem[o_tab + e];
   double* red = s_buf;  // reuse: [PP][n][n] then [PP][n]
 #pragma unroll
   for (int jj = 0; jj < NJ; ++jj) {
@@ -381,62 +416,79 @@ ik_estep_kernel(const EstepArgs a) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int kg_for(int K) {
-  if (K <= 16) return 2;
-  if (K <= 32) return 4;
-  if (K <= 64) return 8;
-  if (K <= 72) return 9;
-  if (K <= 104) return 13;
-  return 16;
-}
+static int kg_for(int K) { return (K + kLanesPerRow - 1) / kLanesPerRow; }
 
 struct EstepPlan {
-  int KG, KS, B, NC, threads, grid;
+  int KG, KS, PP, B, NC, threads, grid, tab;
   size_t smem;
   int64_t cta_scratch;  // doubles
 };
 
-static size_t estep_smem(int KS, int B, int n, int K) {
-  return ((size_t)kPairsPerCta * B * n * KS + 2 * kPairsPerCta * NQ * kNMax + kNMax * kNMax +
-          2 * kNMax + 2 * kPairsPerCta * K) * sizeof(double);
+static size_t estep_fixed_smem(int PP, int K, int P, int Tmax, int tab) {
+  return ((size_t)2 * PP * NQ * kNMax + kNMax * kNMax + 2 * kNMax + (size_t)2 * PP * K +
+          (tab ? (size_t)P * K : 0)) * sizeof(double) + (size_t)PP * Tmax * sizeof(int) + 64;
 }
 
-static EstepPlan plan_bucket(int n, int K, int Tmax, int64_t npairs) {
+static EstepPlan plan_bucket(int n, int K, int P, int Tmax, int64_t npairs) {
   EstepPlan pl;
   pl.KG = kg_for(K);
   pl.KS = pl.KG * kLanesPerRow;
-  size_t slice = (size_t)kPairsPerCta * n * pl.KS * sizeof(double);
-  int B = (int)((44 * 1024) / slice);
+  pl.PP = kPairsPerCta;
+  pl.tab = ((size_t)P * K * sizeof(double) <= 64 * 1024) ? 1 : 0;
+  const size_t fixed = estep_fixed_smem(pl.PP, K, P, Tmax, pl.tab);
+  const size_t slice = (size_t)pl.PP * n * pl.KS * sizeof(double);
+  pl.threads = pl.PP * n * kLanesPerRow;
+  // aim for 3 co-resident CTAs per SM, at least 2 alpha slices per block, at most BMAX
+  const size_t smem_sm = 224 * 1024;
+  int target = 3;
+  int B = 0;
+  for (; target >= 1; --target) {
+    size_t budget = smem_sm / target;
+    if (budget <= fixed + 1024) continue;
+    B = (int)((budget - fixed - 1024) / slice);
+    if (B >= 2 || target == 1) break;
+  }
   if (B < 1) B = 1;
-  if (B > 8) B = 8;
+  if (B > BMAX) B = BMAX;
   if (B > Tmax) B = Tmax > 0 ? Tmax : 1;
   pl.B = B;
   pl.NC = (Tmax + B - 1) / B;
   if (pl.NC < 1) pl.NC = 1;
-  pl.threads = kPairsPerCta * n * kLanesPerRow;
-  pl.smem = estep_smem(pl.KS, B, n, K);
-  int64_t nquads = (npairs + kPairsPerCta - 1) / kPairsPerCta;
-  int per_sm = (int)((220 * 1024) / (pl.smem + 1024));
+  pl.smem = fixed + (size_t)B * slice;
+  int64_t nquads = (npairs + pl.PP - 1) / pl.PP;
+  int per_sm = (int)(smem_sm / (pl.smem + 1024));
   int by_threads = 2048 / pl.threads;
+  int by_regs = 65536 / ((n <= 8 ? 128 : 64) * pl.threads);
   if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm > by_regs) per_sm = by_regs;
   if (per_sm > kEstepCtasPerSm) per_sm = kEstepCtasPerSm;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > nquads) grid = nquads;
   if (grid < 1) grid = 1;
   pl.grid = (int)grid;
-  pl.cta_scratch = (int64_t)kPairsPerCta * ((int64_t)pl.NC * n * pl.KS + (int64_t)Tmax * 2 * n);
+  pl.cta_scratch = (int64_t)pl.PP * ((int64_t)pl.NC * n * pl.KS + (int64_t)Tmax * 2 * n);
   return pl;
 }
 
-template <int KG>
+template <int KG, int NJ, int PP, bool TAB>
 static int launch_estep(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
-  auto kern = ik_estep_kernel<KG>;
+  auto kern = ik_estep_kernel<KG, NJ, PP, TAB>;
   MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem));
   kern<<<pl.grid, pl.threads, pl.smem, st>>>(args);
   MWD_CHECK_LAUNCH();
   return 0;
+}
+
+template <int KG>
+static int launch_estep_kg(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
+  if (args.n <= 8) {
+    if (pl.tab) return launch_estep<KG, 1, kPairsPerCta, true>(args, pl, st);
+    return launch_estep<KG, 1, kPairsPerCta, false>(args, pl, st);
+  }
+  if (pl.tab) return launch_estep<KG, 2, kPairsPerCta, true>(args, pl, st);
+  return launch_estep<KG, 2, kPairsPerCta, false>(args, pl, st);
 }
 
 }  // namespace mwd
@@ -448,7 +500,7 @@ extern "C" int64_t mwd_ik_scratch_bytes(const mwd_ik_problem* p) {
   for (int b = 0; b < p->n_buckets; ++b) {
     int64_t np_ = p->bucket_lo[b + 1] - p->bucket_lo[b];
     if (np_ <= 0) continue;
-    EstepPlan pl = plan_bucket(p->bucket_n[b], p->n_concepts, p->bucket_tmax[b], np_);
+    EstepPlan pl = plan_bucket(p->bucket_n[b], p->n_concepts, p->n_phone_types, p->bucket_tmax[b], np_);
     int64_t bytes = pl.cta_scratch * pl.grid * (int64_t)sizeof(double);
     if (bytes > need) need = bytes;
   }
@@ -464,9 +516,9 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     const int64_t lo = p->bucket_lo[b], hi = p->bucket_lo[b + 1];
     if (hi <= lo) continue;
     MWD_REQUIRE(n >= 1 && n <= MWD_NMAX, "bucket %d: n=%d outside [1,%d]", b, n, MWD_NMAX);
-    EstepPlan pl = plan_bucket(n, p->n_concepts, p->bucket_tmax[b], hi - lo);
-    MWD_REQUIRE(pl.smem <= 227 * 1024, "estep shared memory %zu exceeds 227 KB (n=%d K=%d)",
-                pl.smem, n, p->n_concepts);
+    EstepPlan pl = plan_bucket(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo);
+    MWD_REQUIRE(pl.smem <= 227 * 1024, "estep shared memory %zu exceeds 227 KB (n=%d K=%d T=%d)",
+                pl.smem, n, p->n_concepts, p->bucket_tmax[b]);
     MWD_REQUIRE(ll_only || pl.cta_scratch * pl.grid * (int64_t)sizeof(double) <= p->scratch_bytes,
                 "estep scratch too small: need %lld bytes, have %lld",
                 (long long)(pl.cta_scratch * pl.grid * (int64_t)sizeof(double)),
@@ -499,12 +551,13 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     a.ll_only = ll_only;
     int rc = 0;
     switch (pl.KG) {
-      case 2: rc = launch_estep<2>(a, pl, st); break;
-      case 4: rc = launch_estep<4>(a, pl, st); break;
-      case 8: rc = launch_estep<8>(a, pl, st); break;
-      case 9: rc = launch_estep<9>(a, pl, st); break;
-      case 13: rc = launch_estep<13>(a, pl, st); break;
-      default: rc = launch_estep<16>(a, pl, st); break;
+#define MWD_KG(G) case G: rc = launch_estep_kg<G>(a, pl, st); break;
+      MWD_KG(1) MWD_KG(2) MWD_KG(3) MWD_KG(4) MWD_KG(5) MWD_KG(6) MWD_KG(7) MWD_KG(8)
+      MWD_KG(9) MWD_KG(10) MWD_KG(11) MWD_KG(12) MWD_KG(13) MWD_KG(14) MWD_KG(15) MWD_KG(16)
+#undef MWD_KG
+      default:
+        set_error("n_concepts %d needs KG=%d > 16", p->n_concepts, pl.KG);
+        return 2;
     }
     if (rc) return rc;
   }
