@@ -3,103 +3,152 @@
 //   K3: softmaxLayer, hmm_dnn/image_phone_hmm_word_discoverer.py:533-541 (linear) and
 //       hmm_dnn/image_phone_gaussian_hmm_word_discoverer.py:501-510 (RBF; expanded to
 //       (2 v.mu_k - |mu_k|^2)/width, the row constant -|v|^2/width cancels in the softmax).
-//       regions x concepts GEMM  pz = softmax_rows([V,1] W^T), float64 accumulate.
+//       regions x concepts GEMM  pz = softmax_rows([V,1] W^T).
 //   K4: updateSoftmaxWeight, :475-488 / gaussian :488-499:
 //       grad = (conceptCounts - pz)^T [V,1]  (K x (D+1)), split over rows of V into
 //       kGradSplits deterministic partials that are then summed in fixed order.
 //
-// Both are float64 SIMT GEMMs (DFMA pipe): at K=65, D=512 the two GEMMs are ~1/3 of the
-// iteration's float64 work; 1e-5 parity on W over tens of EM iterations rules out TF32/BF16
-// tensor-core inputs, and B200's FP64 tensor rate equals its DFMA rate.
+// Both GEMMs run on the FP64 tensor path (mma.sync.m8n8k4.f64, "DMMA"): float64 inputs and
+// float64 accumulation, i.e. bit-for-bit the precision class of the reference's NumPy matmul.
+// 1e-5 parity of W over tens of EM iterations rules out TF32/BF16 operands; tcgen05 has no
+// float64 kind, so mma.sync is the tensor instruction that applies here.  One DMMA retires
+// 256 MACs per warp instruction versus 32 for a DFMA, which is what lifts these kernels off the
+// issue-slot limit of the SIMT version.
 #include "mwd_common.cuh"
 
 namespace mwd {
 
-constexpr int BM = 64;   // rows (regions) per CTA tile
-constexpr int BK = 16;   // reduction chunk
-constexpr int TM = 4;    // rows per thread
-// thread grid: 16 (columns, tx) x 16 (rows, ty); thread owns rows ty*4..+3, cols tx + 16*jn
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int BK = 16;        // reduction chunk (feature dims for K3, rows for K4 sub-steps)
+constexpr int LDS_PAD = 20;   // row stride (doubles) of a 16-wide fp64 smem tile: 160 B == 32 mod 128
 
 template <typename FT>
-__device__ __forceinline__ double load_feat(const FT* p) { return (double)(*p); }
+__device__ __forceinline__ double load_feat(const FT* p) { return (double)__ldg(p); }
 
 // ------------------------------------------------------------------------------ K3
-template <int TN, typename FT>
-__global__ void __launch_bounds__(256)
+// CTA = 8 warps; warp w owns rows [w*8*MT, (w+1)*8*MT) of the CTA's 64*MT-row tile and all
+// NT*8 concept columns: MT*NT accumulator fragments (2 doubles each).  The next 16-wide chunk of
+// V (raw element type) and W is prefetched into registers while the DMMAs of the current chunk
+// run; the fp32->fp64 conversion happens only when the registers are staged into shared memory.
+template <int NT, int MT, typename FT>
+__global__ void __launch_bounds__(256, (NT * MT <= 18) ? 2 : 1)
 posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* __restrict__ W,
                  int K, double* __restrict__ pz) {
-  constexpr int KP = 16 * TN;  // padded concept count
-  __shared__ double sV[BK][BM + 4];
-  __shared__ double sW[BK][KP];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  constexpr int BM = 64 * MT;
+  constexpr int KP = 8 * NT;
+  __shared__ double sV[BM * LDS_PAD];
+  __shared__ double sW[KP * LDS_PAD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
   const int64_t row0 = (int64_t)blockIdx.x * BM;
   const int ldw = D + 1;
 
-  double acc[TM][TN];
+  double acc[MT][NT][2];
 #pragma unroll
-  for (int m = 0; m < TM; ++m)
+  for (int m = 0; m < MT; ++m)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[m][j] = 0.0;
+    for (int j = 0; j < NT; ++j) acc[m][j][0] = acc[m][j][1] = 0.0;
 
+  constexpr int VPT = BM / 16;               // V elements per thread per chunk (row = tid/16 + 16 q)
+  constexpr int WPT = (KP + 15) / 16;        // W elements per thread per chunk (k   = tid/16 + 16 q)
+  FT vreg[VPT];
+  double wreg[WPT];
+  const int dd = tid & 15, rr = tid >> 4;
+  // per-thread base pointers; rows/concepts past the end are clamped (loaded, then zeroed)
+  const FT* vptr[VPT];
+  bool vok[VPT];
+#pragma unroll
+  for (int q = 0; q < VPT; ++q) {
+    int64_t gr = row0 + rr + 16 * q;
+    vok[q] = gr < R;
+    vptr[q] = feats + (vok[q] ? gr : 0) * D + dd;
+  }
+  const double* wptr[WPT];
+  bool wok[WPT];
+#pragma unroll
+  for (int q = 0; q < WPT; ++q) {
+    int k = rr + 16 * q;
+    wok[q] = k < K;
+    wptr[q] = W + (size_t)(wok[q] ? k : 0) * ldw + dd;
+  }
+
+  auto fetch = [&](int d0) {
+    const bool dok = d0 + dd < D;
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) vreg[q] = (vok[q] && dok) ? __ldg(vptr[q] + d0) : FT(0);
+#pragma unroll
+    for (int q = 0; q < WPT; ++q) wreg[q] = (wok[q] && dok) ? __ldg(wptr[q] + d0) : 0.0;
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) sV[(rr + 16 * q) * LDS_PAD + dd] = (double)vreg[q];
+#pragma unroll
+    for (int q = 0; q < WPT; ++q)
+      if (rr + 16 * q < KP) sW[(rr + 16 * q) * LDS_PAD + dd] = wreg[q];
+  };
+
+  fetch(0);
   for (int d0 = 0; d0 < D; d0 += BK) {
-    // V tile: 64 rows x 16 d; thread loads 4 elements (row = e/16, dd = e%16 -> coalesced over d)
-#pragma unroll
-    for (int e = threadIdx.x; e < BM * BK; e += 256) {
-      int r = e >> 4, dd = e & 15;
-      int64_t gr = row0 + r;
-      int d = d0 + dd;
-      sV[dd][r] = (gr < R && d < D) ? load_feat(feats + gr * D + d) : 0.0;
-    }
-    for (int e = threadIdx.x; e < KP * BK; e += 256) {
-      int k = e >> 4, dd = e & 15;
-      int d = d0 + dd;
-      sW[dd][k] = (k < K && d < D) ? W[(size_t)k * ldw + d] : 0.0;
-    }
+    stage();
     __syncthreads();
+    if (d0 + BK < D) fetch(d0 + BK);   // next chunk's global loads fly during the DMMAs
 #pragma unroll
-    for (int dd = 0; dd < BK; ++dd) {
-      double v[TM], w[TN];
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double af[MT], bf[NT];
 #pragma unroll
-      for (int m = 0; m < TM; ++m) v[m] = sV[dd][ty * TM + m];
+      for (int m = 0; m < MT; ++m) af[m] = sV[((warp * MT + m) * 8 + g4) * LDS_PAD + kk * 4 + l4];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) w[j] = sW[dd][tx + 16 * j];
+      for (int j = 0; j < NT; ++j) bf[j] = sW[(j * 8 + g4) * LDS_PAD + kk * 4 + l4];
 #pragma unroll
-      for (int m = 0; m < TM; ++m)
+      for (int m = 0; m < MT; ++m)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[m][j] = fma(v[m], w[j], acc[m][j]);
+        for (int j = 0; j < NT; ++j) dmma(acc[m][j][0], acc[m][j][1], af[m], bf[j]);
     }
     __syncthreads();
   }
-  // bias, then exp(x - logsumexp(x)) per row (scipy.special.logsumexp: max-shifted)
+  // epilogue: + bias, exp(x - logsumexp(x)) per row (scipy.special.logsumexp is max-shifted).
+  // Fragment layout: lane holds row g4, columns j*8 + l4*2 + {0,1}; the 4 lanes l4=0..3 of a
+  // group share the row.
 #pragma unroll
-  for (int m = 0; m < TM; ++m) {
+  for (int m = 0; m < MT; ++m) {
     double mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      int k = tx + 16 * j;
-      if (k < K) {
-        acc[m][j] += W[(size_t)k * ldw + D];
-        mx = fmax(mx, acc[m][j]);
-      }
-    }
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
-    for (int s = 8; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+      for (int h = 0; h < 2; ++h) {
+        int k = j * 8 + l4 * 2 + h;
+        if (k < K) {
+          acc[m][j][h] += __ldg(W + (size_t)k * ldw + D);
+          mx = fmax(mx, acc[m][j][h]);
+        }
+      }
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     double sum = 0.0;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      int k = tx + 16 * j;
-      if (k < K) sum += exp(acc[m][j] - mx);
-    }
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
-    for (int s = 8; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+      for (int h = 0; h < 2; ++h) {
+        int k = j * 8 + l4 * 2 + h;
+        if (k < K) sum += exp(acc[m][j][h] - mx);
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     const double lse = log(sum) + mx;
-    const int64_t gr = row0 + ty * TM + m;
+    const int64_t gr = row0 + (warp * MT + m) * 8 + g4;
     if (gr < R) {
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        int k = tx + 16 * j;
-        if (k < K) pz[gr * K + k] = exp(acc[m][j] - lse);
-      }
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int k = j * 8 + l4 * 2 + h;
+          if (k < K) pz[gr * K + k] = exp(acc[m][j][h] - lse);
+        }
     }
   }
 }
@@ -126,16 +175,17 @@ __global__ void gaussian_expand_kernel(const double* __restrict__ mus, int K, in
   }
 }
 
-template <int TN>
+template <int NT>
 static int launch_posterior(const void* feats, int is64, int64_t R, int D, const double* W, int K,
                             double* pz, cudaStream_t st) {
   if (R <= 0) return 0;
-  int64_t grid = (R + BM - 1) / BM;
+  constexpr int MT = (NT <= 9) ? 2 : 1;
+  int64_t grid = (R + 64 * MT - 1) / (64 * MT);
   MWD_REQUIRE(grid <= 0x7fffffff, "too many regions for one launch");
   if (is64)
-    posterior_kernel<TN, double><<<(unsigned)grid, 256, 0, st>>>((const double*)feats, R, D, W, K, pz);
+    posterior_kernel<NT, MT, double><<<(unsigned)grid, 256, 0, st>>>((const double*)feats, R, D, W, K, pz);
   else
-    posterior_kernel<TN, float><<<(unsigned)grid, 256, 0, st>>>((const float*)feats, R, D, W, K, pz);
+    posterior_kernel<NT, MT, float><<<(unsigned)grid, 256, 0, st>>>((const float*)feats, R, D, W, K, pz);
   MWD_CHECK_LAUNCH();
   return 0;
 }
@@ -143,88 +193,125 @@ static int launch_posterior(const void* feats, int is64, int64_t R, int D, const
 static int posterior_dispatch(const void* feats, int is64, int64_t R, int D, const double* W, int K,
                               double* pz, cudaStream_t st) {
   MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "n_concepts %d outside [1,%d]", K, MWD_KMAX);
-  switch ((K + 15) / 16) {
-    case 1: return launch_posterior<1>(feats, is64, R, D, W, K, pz, st);
-    case 2: return launch_posterior<2>(feats, is64, R, D, W, K, pz, st);
-    case 3: return launch_posterior<3>(feats, is64, R, D, W, K, pz, st);
-    case 4: return launch_posterior<4>(feats, is64, R, D, W, K, pz, st);
-    case 5: return launch_posterior<5>(feats, is64, R, D, W, K, pz, st);
-    case 6: return launch_posterior<6>(feats, is64, R, D, W, K, pz, st);
-    case 7: return launch_posterior<7>(feats, is64, R, D, W, K, pz, st);
-    default: return launch_posterior<8>(feats, is64, R, D, W, K, pz, st);
+  switch ((K + 7) / 8) {
+#define MWD_NT(T) case T: return launch_posterior<T>(feats, is64, R, D, W, K, pz, st);
+    MWD_NT(1) MWD_NT(2) MWD_NT(3) MWD_NT(4) MWD_NT(5) MWD_NT(6) MWD_NT(7) MWD_NT(8)
+    MWD_NT(9) MWD_NT(10) MWD_NT(11) MWD_NT(12) MWD_NT(13) MWD_NT(14) MWD_NT(15) MWD_NT(16)
+#undef MWD_NT
   }
+  set_error("n_concepts %d not supported", K);
+  return 2;
 }
 
 // ------------------------------------------------------------------------------ K4
 // partial[s][k][d] = sum_{r in split s} (cC - pz)[r][k] * [V,1][r][d]
-constexpr int BD = 64;   // feature columns per CTA tile (thread: 4 consecutive d)
-constexpr int BR = 16;   // rows per smem chunk
+// CTA tile: all K concepts (MT8 = ceil(K/8) m-tiles) x 128 feature columns; warp w owns the 16
+// feature columns [w*16, w*16+16) (2 n-tiles) and all m-tiles: 2*MT8 accumulator fragments, 2+MT8
+// fragment loads per 2*MT8 DMMAs.  The reduction runs over rows in chunks of 16 with register
+// prefetch of the next chunk.  The bias column d == D ([V,1]'s ones) is the column sum of Delta;
+// the blockIdx.x == 0 CTAs accumulate it from the staged Delta tile.
+constexpr int BD = 128;
+constexpr int BR = 16;
 
-template <int TN, typename FT>
-__global__ void __launch_bounds__(256)
+template <int MT8, typename FT>
+__global__ void __launch_bounds__(256, (MT8 <= 9) ? 2 : 1)
 posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* __restrict__ cC,
                       const double* __restrict__ pz, int K, int64_t rows_per_split,
                       double* __restrict__ partial) {
-  constexpr int KP = 16 * TN;
-  __shared__ double sDl[BR][KP];       // Delta tile
-  __shared__ double sV[BR][BD + 4];
-  const int tx = threadIdx.x & 15;     // concept direction: k = tx + 16*j
-  const int ty = threadIdx.x >> 4;     // feature direction: d = d0 + ty*4 + m
+  constexpr int KP = 8 * MT8;
+  constexpr int LDD = KP + 4;            // Delta tile [BR][KP], padded: 608 B == 96 mod 128 (KP=72)
+  constexpr int LDV = BD + 4;            // V tile [BR][BD], padded: 1056 B == 32 mod 128
+  __shared__ double sDl[BR * LDD];
+  __shared__ double sV[BR * LDV];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
   const int d0 = blockIdx.x * BD;
   const int split = blockIdx.y;
   const int64_t rbeg = (int64_t)split * rows_per_split;
   const int64_t rend = min(R, rbeg + rows_per_split);
   const int ld = D + 1;
+  const bool do_bias = (blockIdx.x == 0);
 
-  double acc[TN][TM];
+  double acc[MT8][2][2];
 #pragma unroll
-  for (int j = 0; j < TN; ++j)
+  for (int m = 0; m < MT8; ++m)
 #pragma unroll
-    for (int m = 0; m < TM; ++m) acc[j][m] = 0.0;
+    for (int j = 0; j < 2; ++j) acc[m][j][0] = acc[m][j][1] = 0.0;
+  double bias_acc = 0.0;
 
-  for (int64_t r0 = rbeg; r0 < rend; r0 += BR) {
-    for (int e = threadIdx.x; e < BR * KP; e += 256) {
+  // Delta tile: BR*KP elements, thread handles element e = tid + 256 q -> (row e / KP, k e % KP)
+  constexpr int DPT = (BR * KP + 255) / 256;
+  // V tile: BR*BD elements, thread handles column tid & 127, rows (tid >> 7) + 2 q
+  constexpr int VPT = BR / 2;
+  double dreg[DPT];
+  FT vreg[VPT];
+  const int vcol = tid & 127, vrow = tid >> 7;
+  const bool vcol_ok = d0 + vcol < D;
+
+  auto fetch = [&](int64_t r0) {
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+      int e = tid + 256 * q;
       int rr = e / KP, k = e - rr * KP;
       int64_t r = r0 + rr;
-      sDl[rr][k] = (r < rend && k < K) ? (cC[r * K + k] - pz[r * K + k]) : 0.0;
+      dreg[q] = (e < BR * KP && r < rend && k < K) ? (__ldg(cC + r * K + k) - __ldg(pz + r * K + k)) : 0.0;
     }
-    for (int e = threadIdx.x; e < BR * BD; e += 256) {
-      int rr = e >> 6, dd = e & 63;
-      int64_t r = r0 + rr;
-      int d = d0 + dd;
-      double v = 0.0;
-      if (r < rend) {
-        if (d < D) v = load_feat(feats + r * D + d);
-        else if (d == D) v = 1.0;
-      }
-      sV[rr][dd] = v;
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      int64_t r = r0 + vrow + 2 * q;
+      vreg[q] = (vcol_ok && r < rend) ? __ldg(feats + r * D + d0 + vcol) : FT(0);
     }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+      int e = tid + 256 * q;
+      int rr = e / KP, k = e - rr * KP;
+      if (e < BR * KP) sDl[rr * LDD + k] = dreg[q];
+    }
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) sV[(vrow + 2 * q) * LDV + vcol] = (double)vreg[q];
+  };
+
+  if (rbeg < rend) fetch(rbeg);
+  for (int64_t r0 = rbeg; r0 < rend; r0 += BR) {
+    stage();
     __syncthreads();
+    if (r0 + BR < rend) fetch(r0 + BR);
 #pragma unroll
-    for (int rr = 0; rr < BR; ++rr) {
-      double dl[TN], v[TM];
+    for (int kk = 0; kk < BR / 4; ++kk) {
+      // A = Delta^T fragment: A[k = m*8+g4][r = kk*4+l4];  B = V fragment: B[r = kk*4+l4][d = warp*16 + j*8 + g4]
+      double bf[2];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) dl[j] = sDl[rr][tx + 16 * j];
+      for (int j = 0; j < 2; ++j) bf[j] = sV[(kk * 4 + l4) * LDV + warp * 16 + j * 8 + g4];
 #pragma unroll
-      for (int m = 0; m < TM; ++m) v[m] = sV[rr][ty * TM + m];
+      for (int m = 0; m < MT8; ++m) {
+        const double af = sDl[(kk * 4 + l4) * LDD + m * 8 + g4];
 #pragma unroll
-      for (int j = 0; j < TN; ++j)
+        for (int j = 0; j < 2; ++j) dmma(acc[m][j][0], acc[m][j][1], af, bf[j]);
+      }
+    }
+    if (do_bias && tid < KP) {
 #pragma unroll
-        for (int m = 0; m < TM; ++m) acc[j][m] = fma(dl[j], v[m], acc[j][m]);
+      for (int rr = 0; rr < BR; ++rr) bias_acc += sDl[rr * LDD + tid];
     }
     __syncthreads();
   }
+  // C fragment: row k = m*8 + g4, cols d = d0 + warp*16 + j*8 + l4*2 + {0,1}
   double* out = partial + (size_t)split * K * ld;
 #pragma unroll
-  for (int j = 0; j < TN; ++j) {
-    int k = tx + 16 * j;
+  for (int m = 0; m < MT8; ++m) {
+    int k = m * 8 + g4;
     if (k >= K) continue;
 #pragma unroll
-    for (int m = 0; m < TM; ++m) {
-      int d = d0 + ty * TM + m;
-      if (d < ld) out[(size_t)k * ld + d] = acc[j][m];
-    }
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int d = d0 + warp * 16 + j * 8 + l4 * 2 + h;
+        if (d < D) out[(size_t)k * ld + d] = acc[m][j][h];
+      }
   }
+  if (do_bias && tid < K) out[(size_t)tid * ld + D] = bias_acc;
 }
 
 __global__ void grad_reduce_kernel(const double* __restrict__ partial, int splits, int64_t elems,
@@ -236,20 +323,20 @@ __global__ void grad_reduce_kernel(const double* __restrict__ partial, int split
   grad[e] = s;
 }
 
-template <int TN>
+template <int MT8>
 static int launch_grad(const mwd_ik_problem* p, double* partial, cudaStream_t st) {
   const int D = p->feat_dim, K = p->n_concepts;
   const int64_t R = p->n_regions;
   int64_t rps = (R + kGradSplits - 1) / kGradSplits;
   rps = ((rps + BR - 1) / BR) * BR;
   if (rps < BR) rps = BR;
-  dim3 grid((D + 1 + BD - 1) / BD, kGradSplits);
+  dim3 grid((D + BD - 1) / BD, kGradSplits);
   if (p->feat_is_f64)
-    posterior_grad_kernel<TN, double><<<grid, 256, 0, st>>>((const double*)p->feats, R, D,
-                                                            p->concept_counts, p->pz, K, rps, partial);
+    posterior_grad_kernel<MT8, double><<<grid, 256, 0, st>>>((const double*)p->feats, R, D,
+                                                             p->concept_counts, p->pz, K, rps, partial);
   else
-    posterior_grad_kernel<TN, float><<<grid, 256, 0, st>>>((const float*)p->feats, R, D,
-                                                           p->concept_counts, p->pz, K, rps, partial);
+    posterior_grad_kernel<MT8, float><<<grid, 256, 0, st>>>((const float*)p->feats, R, D,
+                                                            p->concept_counts, p->pz, K, rps, partial);
   MWD_CHECK_LAUNCH();
   return 0;
 }
@@ -281,16 +368,12 @@ extern "C" int mwd_ik_posterior_grad(const mwd_ik_problem* p, double* grad_parti
   cudaStream_t st = as_stream(stream);
   const int K = p->n_concepts;
   MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "n_concepts %d outside [1,%d]", K, MWD_KMAX);
-  int rc;
-  switch ((K + 15) / 16) {
-    case 1: rc = launch_grad<1>(p, grad_partials, st); break;
-    case 2: rc = launch_grad<2>(p, grad_partials, st); break;
-    case 3: rc = launch_grad<3>(p, grad_partials, st); break;
-    case 4: rc = launch_grad<4>(p, grad_partials, st); break;
-    case 5: rc = launch_grad<5>(p, grad_partials, st); break;
-    case 6: rc = launch_grad<6>(p, grad_partials, st); break;
-    case 7: rc = launch_grad<7>(p, grad_partials, st); break;
-    default: rc = launch_grad<8>(p, grad_partials, st); break;
+  int rc = 2;
+  switch ((K + 7) / 8) {
+#define MWD_MT(T) case T: rc = launch_grad<T>(p, grad_partials, st); break;
+    MWD_MT(1) MWD_MT(2) MWD_MT(3) MWD_MT(4) MWD_MT(5) MWD_MT(6) MWD_MT(7) MWD_MT(8)
+    MWD_MT(9) MWD_MT(10) MWD_MT(11) MWD_MT(12) MWD_MT(13) MWD_MT(14) MWD_MT(15) MWD_MT(16)
+#undef MWD_MT
   }
   if (rc) return rc;
   const int64_t elems = (int64_t)K * (p->feat_dim + 1);
