@@ -78,3 +78,18 @@ def make_model(tmp, g):
                 ImagePhoneGaussianHMMWordDiscoverer
             m = ImagePhoneGaussianHMMWordDiscoverer(caps, feats, cfg, modelName=os.path.join(tmp, 'm'))
     return m
+
+
+HMM_CASES = ['flickr60_prob', 'flickr24_log', 'synth_prob', 'synth_log']
+
+
+def load_hmm(case):
+    z = np.load(os.path.join(GOLDEN, 'hmm_%s.npz' % case))
+    g = {k: z[k] for k in z.files}
+    to, so = g['tgt_off'], g['src_off']
+    g['tgt_list'] = [g['tgt'][to[i]:to[i + 1]] for i in range(len(to) - 1)]
+    g['src_list'] = [g['src'][so[i]:so[i + 1]] for i in range(len(so) - 1)]
+    g['kind'] = str(g['kind'])
+    for k in ('Vt', 'Vf', 'n_iter'):
+        g[k] = int(g[k])
+    return g
