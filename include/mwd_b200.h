@@ -49,7 +49,8 @@ extern "C" {
 const char* mwd_last_error(void);
 int mwd_version(void);
 /* sizeof() of the ABI structs as compiled (which: 0 mwd_geometry, 1 mwd_ik_problem,
- * 2 mwd_partial_sizes, 3 mwd_ik_mstep_args) -- lets a binding verify its struct mirrors.      */
+ * 2 mwd_partial_sizes, 3 mwd_ik_mstep_args, 4 mwd_hmm_problem, 5 mwd_hmm_mstep_args) -- lets a
+ * binding verify its struct mirrors.                                                        */
 int mwd_abi_sizeof(int which);
 
 /* device / launch geometry the host side needs to size workspaces ------------------------- */
@@ -193,6 +194,82 @@ int mwd_ik_forward_dense(const double* pz_pair, const int32_t* phones_pair, int 
                          double* out, void* stream);
 int mwd_ik_backward_dense(const double* pz_pair, const int32_t* phones_pair, int T, int n, int K,
                           const double* trans, const double* obsT, double* out, void* stream);
+
+/* ============================================================================================
+ * Plain-state HMM word discoverers of hmm/  (states = concept tokens of the caption)
+ *   prob domain: hmm/hmm_word_discoverer.py        HMMWordDiscoverer
+ *   log  domain: hmm/audio_hmm_word_discoverer.py  AudioHMMWordDiscoverer (NULL state first;
+ *                hmm/hmm_word_discoverer_logscale.py is the same code)
+ * The dict-of-dict obs[tw][fw] is a dense (Vt x Vf) table, NaN = pair absent from the dict.
+ * Pairs are sorted by (n states, T) and CSR-packed like the (i,k) model:
+ *   tgt_off[N+1] -> tgt[] concept ids (the states), src_off[N+1] -> src[] phone ids.
+ * Slot (pair p, t, i) of the per-pair posterior buffer lives at slot_off[p] + t*n_p + i.
+ * ============================================================================================ */
+typedef struct {
+  int64_t n_pairs;
+  int64_t n_slots;            /* sum_p T_p * n_p                                             */
+  int32_t n_tgt_types;        /* Vt                                                          */
+  int32_t n_src_types;        /* Vf                                                          */
+  int32_t t_max;
+  int32_t log_domain;         /* 0: HMMWordDiscoverer, 1: AudioHMMWordDiscoverer             */
+  int32_t n_buckets;
+  int32_t reserved;
+  const int32_t* bucket_n;    /* [host]                                                      */
+  const int64_t* bucket_lo;   /* [host] n_buckets+1                                          */
+  const int32_t* bucket_tmax; /* [host]                                                      */
+  const int32_t* tgt_off;     /* [dev] N+1                                                   */
+  const int32_t* tgt;         /* [dev]                                                       */
+  const int32_t* src_off;     /* [dev] N+1                                                   */
+  const int32_t* src;         /* [dev]                                                       */
+  const int64_t* slot_off;    /* [dev] N+1                                                   */
+  const double* init;         /* [dev] (NMAX+1) x NMAX        (log values when log_domain)   */
+  const double* trans;        /* [dev] (NMAX+1) x NMAX*NMAX                                  */
+  const double* obs;          /* [dev] Vt x Vf, NaN = absent                                 */
+  double* pair_ll;            /* [dev] N   log p(f | e) per pair                             */
+  double* post;               /* [dev] n_slots  state posteriors (prob) / normalised log
+                                 posteriors (log) -- input of the postings reduction         */
+  double* part_init;          /* [dev] hmm_warps x (NMAX+1) x NMAX                           */
+  double* part_trans;         /* [dev] hmm_warps x (NMAX+1) x NMAX*NMAX                      */
+  double* alpha_out;          /* [dev] n_slots or NULL: forward()  values                    */
+  double* beta_out;           /* [dev] n_slots or NULL: backward() values                    */
+} mwd_hmm_problem;
+
+/* number of persistent warps (= rows of part_init / part_trans)                              */
+int mwd_hmm_warps(void);
+
+/* forward + backward + updateInitialCounts + updateTransitionCounts + state posteriors:
+ * hmm_word_discoverer.py:110-203 / audio_hmm_word_discoverer.py:148-254 (incl. its quirks:
+ * un-normalised init counts, transition counts from the last t only).  Accumulates into
+ * part_init / part_trans (zero / -inf them first), writes pair_ll and post.                  */
+int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream);
+
+/* Deterministic reduction of the partials and of the posteriors through a static postings
+ * index (post_idx sorted by table entry, post_off[Vt*Vf+1]):
+ *   counts = [ obsC (Vt x Vf) | initC ((NMAX+1) x NMAX) | transC ((NMAX+1) x NMAX^2) | sum LL ]
+ * sums in the prob domain, log-sum-exp in the log domain.                                    */
+int64_t mwd_hmm_counts_len(int n_tgt_types, int n_src_types);
+int mwd_hmm_reduce(const mwd_hmm_problem* p, const int64_t* post_idx, const int64_t* post_off,
+                   double* counts, void* stream);
+
+/* M-step: hmm_word_discoverer.py:275-296 (Toeplitz pooling applied here, it is linear) /
+ * audio_hmm_word_discoverer.py:354-389 (counts first merged into the running log accumulators
+ * `acc`, which persist over epochs like the reference's count lists).                        */
+typedef struct {
+  int32_t log_domain, n_tgt_types, n_src_types, n_lens;
+  const int32_t* lens;        /* [host]                                                      */
+  const double* counts;       /* [dev]                                                       */
+  double* acc;                /* [dev] running log accumulators (log domain only), same layout*/
+  double* init;               /* [dev] in/out                                                */
+  double* trans;              /* [dev] in/out                                                */
+  double* obs;                /* [dev] in/out (NaN entries stay NaN)                         */
+} mwd_hmm_mstep_args;
+int mwd_hmm_mstep(const mwd_hmm_mstep_args* a, void* stream);
+
+/* align: hmm_word_discoverer.py:301-329 / audio_hmm_word_discoverer.py:396-427.
+ *   alignment   [dev] sum_p T_p int32
+ *   align_probs [dev] sum_p (T_p - 1) * n_p doubles or NULL, pair p at ap_off[p]             */
+int mwd_hmm_align(const mwd_hmm_problem* p, double unk_prob, int32_t* alignment, double* align_probs,
+                  const int64_t* ap_off, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,29 @@ class IkMstepArgs(C.Structure):
     ]
 
 
+class HmmProblem(C.Structure):
+    _fields_ = [
+        ('n_pairs', C.c_int64), ('n_slots', C.c_int64),
+        ('n_tgt_types', C.c_int32), ('n_src_types', C.c_int32), ('t_max', C.c_int32),
+        ('log_domain', C.c_int32), ('n_buckets', C.c_int32), ('reserved', C.c_int32),
+        ('bucket_n', C.c_void_p), ('bucket_lo', C.c_void_p), ('bucket_tmax', C.c_void_p),
+        ('tgt_off', C.c_void_p), ('tgt', C.c_void_p), ('src_off', C.c_void_p), ('src', C.c_void_p),
+        ('slot_off', C.c_void_p),
+        ('init', C.c_void_p), ('trans', C.c_void_p), ('obs', C.c_void_p),
+        ('pair_ll', C.c_void_p), ('post', C.c_void_p),
+        ('part_init', C.c_void_p), ('part_trans', C.c_void_p),
+        ('alpha_out', C.c_void_p), ('beta_out', C.c_void_p),
+    ]
+
+
+class HmmMstepArgs(C.Structure):
+    _fields_ = [
+        ('log_domain', C.c_int32), ('n_tgt_types', C.c_int32), ('n_src_types', C.c_int32),
+        ('n_lens', C.c_int32), ('lens', C.c_void_p), ('counts', C.c_void_p), ('acc', C.c_void_p),
+        ('init', C.c_void_p), ('trans', C.c_void_p), ('obs', C.c_void_p),
+    ]
+
+
 # every symbol include/mwd_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 SYMBOLS = {
@@ -77,6 +100,12 @@ SYMBOLS = {
     'mwd_argmax_rows': (_i, [_vp, _i64, _i, _vp, _vp]),
     'mwd_ik_forward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'mwd_ik_backward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'mwd_hmm_warps': (_i, []),
+    'mwd_hmm_estep': (_i, [C.POINTER(HmmProblem), _vp]),
+    'mwd_hmm_counts_len': (_i64, [_i, _i]),
+    'mwd_hmm_reduce': (_i, [C.POINTER(HmmProblem), _vp, _vp, _vp, _vp]),
+    'mwd_hmm_mstep': (_i, [C.POINTER(HmmMstepArgs), _vp]),
+    'mwd_hmm_align': (_i, [C.POINTER(HmmProblem), _d, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -96,7 +125,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    for which, st in enumerate((Geometry, IkProblem, PartialSizes, IkMstepArgs)):
+    for which, st in enumerate((Geometry, IkProblem, PartialSizes, IkMstepArgs, HmmProblem, HmmMstepArgs)):
         if lib.mwd_abi_sizeof(which) != C.sizeof(st):
             raise MwdError('ABI mismatch: %s is %d bytes in libmwd_b200.so, %d in the binding'
                            % (st.__name__, lib.mwd_abi_sizeof(which), C.sizeof(st)))

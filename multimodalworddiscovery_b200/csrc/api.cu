@@ -52,6 +52,8 @@ extern "C" int mwd_abi_sizeof(int which) {
     case 1: return (int)sizeof(mwd_ik_problem);
     case 2: return (int)sizeof(mwd_partial_sizes);
     case 3: return (int)sizeof(mwd_ik_mstep_args);
+    case 4: return (int)sizeof(mwd_hmm_problem);
+    case 5: return (int)sizeof(mwd_hmm_mstep_args);
     default: return -1;
   }
 }

@@ -46,6 +46,14 @@ __global__ void ll_stage2_kernel(const double* __restrict__ blk, double* __restr
   if (threadIdx.x == 0) out[0] = s[0];
 }
 
+// fixed-shape deterministic sum of n doubles (blk_scratch: >= kLLBlocks doubles)
+int sum_doubles(const double* x, int64_t n, double* blk_scratch, double* out, cudaStream_t st) {
+  ll_stage1_kernel<<<kLLBlocks, 256, 0, st>>>(x, n, blk_scratch);
+  ll_stage2_kernel<<<1, kLLBlocks, 0, st>>>(blk_scratch, out);
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
 // init / trans M-step for one m (one CTA per distinct length)
 struct LensArg { int lens[kNMax + 1]; int n; };
 
@@ -155,12 +163,9 @@ extern "C" int mwd_ik_reduce_counts(const mwd_ik_problem* p, double* counts, voi
   reduce_rows_kernel<<<(unsigned)((ie + 255) / 256), 256, 0, st>>>(p->part_init, rows, ie, counts + pe);
   reduce_rows_kernel<<<(unsigned)((te + 255) / 256), 256, 0, st>>>(p->part_trans, rows, te,
                                                                    counts + pe + ie);
-  // log-likelihood: stage-1 partials are parked in the (already consumed) head of part_init
-  double* blk = p->part_init;
-  ll_stage1_kernel<<<kLLBlocks, 256, 0, st>>>(p->pair_ll, p->n_pairs, blk);
-  ll_stage2_kernel<<<1, kLLBlocks, 0, st>>>(blk, counts + pe + ie + te);
   MWD_CHECK_LAUNCH();
-  return 0;
+  // log-likelihood: stage-1 partials are parked in the (already consumed) head of part_init
+  return sum_doubles(p->pair_ll, p->n_pairs, p->part_init, counts + pe + ie + te, st);
 }
 
 extern "C" int mwd_ik_mstep(const mwd_ik_mstep_args* a, void* stream) {

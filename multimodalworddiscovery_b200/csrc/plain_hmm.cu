@@ -1,0 +1,608 @@
+// Plain-state HMM word discoverers of hmm/ (states = concept tokens of the caption).
+//
+//   prob domain: hmm/hmm_word_discoverer.py       forward :110-125, backward :127-138,
+//                updateInitialCounts :140-151, updateTransitionCounts :153-186,
+//                updateObservationCounts :188-203, M-step :275-296, align :301-329
+//   log  domain: hmm/audio_hmm_word_discoverer.py forward :148-168, backward :170-185,
+//                counts :187-254, M-step :354-389, align :396-427
+//
+// Mapping: one warp per caption pair, lane j = state j (n <= 16); alpha history of the pair in
+// shared memory; per-warp register accumulators for the init / transition counts (persistent
+// warps, fixed pair->warp assignment, so the two-level reduction is deterministic); the
+// observation counts go through a static postings index (slots sorted by (concept, phone) table
+// entry) and a segmented reduction -- no atomics anywhere.  The path is latency/HBM-bound
+// (~210 B and ~3.5 kFLOP per pair), so the design goal is many independent warps, not tensor cores.
+#include "mwd_common.cuh"
+
+namespace mwd {
+
+constexpr int kHmmWarpsPerSm = 16;
+
+int hmm_warps_total() { return sm_count() * kHmmWarpsPerSm; }
+
+struct HmmArgs {
+  const int32_t* tgt_off;
+  const int32_t* tgt;
+  const int32_t* src_off;
+  const int32_t* src;
+  const int64_t* slot_off;
+  const double* init;    // row of this n
+  const double* trans;   // table of this n
+  const double* obs;
+  double* pair_ll;
+  double* post;
+  double* part_init;     // full partial tables
+  double* part_trans;
+  double* alpha_out;
+  double* beta_out;
+  int64_t lo, hi;
+  int n, Vf, Tmax, warps_per_cta, total_warps;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+// scipy.special.logsumexp over the lanes (inactive lanes pass -inf)
+__device__ __forceinline__ double warp_lse(double v) {
+  double m = warp_max(v);
+  if (!(fabs(m) < INFINITY)) m = 0.0;
+  double s = warp_sum(exp(v - m));
+  return log(s) + m;
+}
+__device__ __forceinline__ double lse2(double a, double b) {
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  double m = fmax(a, b);
+  return m + log(exp(a - m) + exp(b - m));
+}
+
+template <bool LOG>
+__global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
+  const int n = a.n, Vf = a.Vf;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int j = lane;
+  const bool on = j < n;
+  extern __shared__ double smem[];
+  double* s_A = smem;                       // [n][n]
+  double* s_pi = s_A + kNMax * kNMax;       // [n]
+  const int per_warp = a.Tmax * n + kNMax + kNMax * kNMax;
+  double* s_al = s_pi + kNMax + (size_t)wic * per_warp;   // [Tmax][n]
+  double* s_x = s_al + (size_t)a.Tmax * n;                // [n]
+  double* s_E = s_x + kNMax;                              // [n][n] (log trans counts)
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) s_A[e] = a.trans[e];
+  for (int e = threadIdx.x; e < n; e += blockDim.x) s_pi[e] = a.init[e];
+  __syncthreads();
+
+  const double ident = LOG ? -INFINITY : 0.0;
+  double init_acc = ident;
+  double tacc[kNMax];
+#pragma unroll
+  for (int i = 0; i < kNMax; ++i) tacc[i] = ident;
+
+  const int gw = blockIdx.x * a.warps_per_cta + wic;
+  if (wic < a.warps_per_cta) {
+    for (int64_t pair = a.lo + gw; pair < a.hi; pair += a.total_warps) {
+      const int f0 = a.src_off[pair];
+      const int T = a.src_off[pair + 1] - f0;
+      const int32_t* f = a.src + f0;
+      const int ej = on ? a.tgt[a.tgt_off[pair] + j] : 0;
+      const double* orow = a.obs + (size_t)ej * Vf;
+      const int64_t slot0 = a.slot_off[pair];
+      auto emis = [&](int t) -> double {
+        double b = on ? orow[f[t]] : 0.0;
+        return (b != b) ? 0.0 : b;           // absent pair: 0 in both classes (:122 / :161)
+      };
+      // ------------------------------------------------------------ forward
+      double al;
+      {
+        double b0 = on ? orow[f[0]] : 0.0;
+        if (LOG) al = on ? s_pi[j] + b0 : -INFINITY;          // :158 (absent -> KeyError upstream)
+        else al = on ? s_pi[j] * ((b0 != b0) ? 0.0 : b0) : 0.0;   // :114-118
+      }
+      if (on) s_al[j] = al;
+      for (int t = 0; t + 1 < T; ++t) {
+        __syncwarp();
+        const double b = emis(t + 1);
+        const double* at = s_al + (size_t)t * n;
+        if (LOG) {
+          double m = -INFINITY;
+          for (int i = 0; i < n; ++i) m = fmax(m, s_A[i * n + (on ? j : 0)] + at[i]);
+          if (!(fabs(m) < INFINITY)) m = 0.0;
+          double s = 0.0;
+          for (int i = 0; i < n; ++i) s += exp(s_A[i * n + (on ? j : 0)] + at[i] - m);
+          al = log(s) + m + b;                                 // :165
+        } else {
+          double acc = 0.0;
+          for (int i = 0; i < n; ++i) acc = fma(s_A[i * n + (on ? j : 0)], at[i], acc);
+          al = acc * b;                                        // :123
+        }
+        if (on) s_al[(size_t)(t + 1) * n + j] = al;
+      }
+      __syncwarp();
+      double ll;
+      {
+        double last = on ? s_al[(size_t)(T - 1) * n + j] : (LOG ? -INFINITY : 0.0);
+        ll = LOG ? warp_lse(last) : log(warp_sum(last));       // :312 / :244-245
+      }
+      if (lane == 0) a.pair_ll[pair] = ll;
+      // ------------------------------------------------------------ backward + counts
+      if (LOG) {
+        if (T >= 2) {   // transition counts from the LAST t only (:204-229)
+          const double bl = emis(T - 1);
+          for (int i = 0; i < n; ++i)
+            if (on) s_E[i * n + j] = s_al[(size_t)(T - 2) * n + i] + s_A[i * n + j] + bl;   // beta_{T-1} = 0
+          __syncwarp();
+          if (on) {
+            for (int i = 0; i < n; ++i) {
+              const int dlt = j - i;
+              double m = -INFINITY;
+              for (int r = 0; r < n; ++r) {
+                int c = r + dlt;
+                if (c >= 0 && c < n) m = fmax(m, s_E[r * n + c]);
+              }
+              if (!(fabs(m) < INFINITY)) m = 0.0;
+              double s = 0.0;
+              for (int r = 0; r < n; ++r) {
+                int c = r + dlt;
+                if (c >= 0 && c < n) s += exp(s_E[r * n + c] - m);
+              }
+              tacc[i] = lse2(tacc[i], log(s) + m);
+            }
+          }
+          __syncwarp();
+        }
+        double beta = on ? 0.0 : -INFINITY;
+        double ic = -INFINITY, nrm = -INFINITY;
+        for (int t = T - 1; t >= 0; --t) {
+          const double alv = on ? s_al[(size_t)t * n + j] : -INFINITY;
+          const double v = on ? alv + beta : -INFINITY;
+          if (a.alpha_out && on) { a.alpha_out[slot0 + (int64_t)t * n + j] = alv; a.beta_out[slot0 + (int64_t)t * n + j] = beta; }
+          ic = lse2(ic, v);
+          nrm = lse2(nrm, warp_lse(v));
+          if (on) s_al[(size_t)t * n + j] = v;
+          if (t > 0) {
+            const double bb = beta + emis(t);
+            if (on) s_x[j] = bb;
+            __syncwarp();
+            double m = -INFINITY;
+            for (int c = 0; c < n; ++c) m = fmax(m, s_A[(on ? j : 0) * n + c] + s_x[c]);
+            if (!(fabs(m) < INFINITY)) m = 0.0;
+            double s = 0.0;
+            for (int c = 0; c < n; ++c) s += exp(s_A[(on ? j : 0) * n + c] + s_x[c] - m);
+            beta = on ? log(s) + m : -INFINITY;                // :182
+            __syncwarp();
+          }
+        }
+        init_acc = lse2(init_acc, ic);                         // :192-194
+        __syncwarp();
+        for (int t = 0; t < T; ++t)
+          if (on) a.post[slot0 + (int64_t)t * n + j] = s_al[(size_t)t * n + j] - nrm;   // :244-246
+        __syncwarp();
+      } else {
+        double beta = on ? 1.0 : 0.0;
+        for (int t = T - 1; t >= 0; --t) {
+          const double alv = on ? s_al[(size_t)t * n + j] : 0.0;
+          const double g = alv * beta;
+          const double G = warp_sum(g);
+          const double gam = g / G;                            // :147-148, :193
+          if (on) {
+            init_acc += gam;
+            a.post[slot0 + (int64_t)t * n + j] = gam;
+            if (a.alpha_out) { a.alpha_out[slot0 + (int64_t)t * n + j] = alv; a.beta_out[slot0 + (int64_t)t * n + j] = beta; }
+          }
+          if (t > 0) {
+            const double bb = beta * emis(t);
+            // xi_{t-1}[i][j] = (alpha_{t-1}[i] * bb[j]) * A[i][j], normalised over (i, j)  (:161-162)
+            const double* ap = s_al + (size_t)(t - 1) * n;
+            double xv[kNMax];
+            double col = 0.0;
+#pragma unroll
+            for (int i = 0; i < kNMax; ++i) {
+              xv[i] = (i < n && on) ? (ap[i] * bb) * s_A[i * n + j] : 0.0;
+              col += xv[i];
+            }
+            const double Z = warp_sum(col);
+#pragma unroll
+            for (int i = 0; i < kNMax; ++i) tacc[i] += xv[i] / Z;
+            if (on) s_x[j] = bb;
+            __syncwarp();
+            double acc = 0.0;
+            for (int c = 0; c < n; ++c) acc = fma(s_A[(on ? j : 0) * n + c], s_x[c], acc);
+            beta = on ? acc : 0.0;                             // :136
+            __syncwarp();
+          }
+        }
+      }
+    }
+    // per-warp partial rows (one row per persistent warp and per n)
+    if (on) {
+      a.part_init[((size_t)gw * (kNMax + 1) + n) * kNMax + j] = init_acc;
+      double* pt = a.part_trans + ((size_t)gw * (kNMax + 1) + n) * (kNMax * kNMax);
+#pragma unroll
+      for (int i = 0; i < kNMax; ++i)
+        if (i < n) pt[i * n + j] = tacc[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- reductions
+template <bool LOG>
+__global__ void hmm_reduce_rows_kernel(const double* __restrict__ part, int rows, int64_t elems,
+                                       double* __restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  if (LOG) {
+    double m = -INFINITY;
+    for (int r = 0; r < rows; ++r) m = fmax(m, part[(size_t)r * elems + e]);
+    if (m == -INFINITY) { out[e] = -INFINITY; return; }
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += exp(part[(size_t)r * elems + e] - m);
+    out[e] = log(s) + m;
+  } else {
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += part[(size_t)r * elems + e];
+    out[e] = s;
+  }
+}
+
+// one warp per (concept, phone) table entry, over its postings
+template <bool LOG>
+__global__ void hmm_postings_kernel(const double* __restrict__ post, const int64_t* __restrict__ idx,
+                                    const int64_t* __restrict__ off, int64_t entries,
+                                    double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= entries) return;
+  const int64_t lo = off[e], hi = off[e + 1];
+  if (LOG) {
+    double m = -INFINITY;
+    for (int64_t q = lo + lane; q < hi; q += 32) m = fmax(m, post[idx[q]]);
+    m = warp_max(m);
+    if (m == -INFINITY) { if (lane == 0) out[e] = -INFINITY; return; }
+    double s = 0.0;
+    for (int64_t q = lo + lane; q < hi; q += 32) s += exp(post[idx[q]] - m);
+    s = warp_sum(s);
+    if (lane == 0) out[e] = log(s) + m;
+  } else {
+    double s = 0.0;
+    for (int64_t q = lo + lane; q < hi; q += 32) s += post[idx[q]];
+    s = warp_sum(s);
+    if (lane == 0) out[e] = s;
+  }
+}
+
+// ---------------------------------------------------------------- M-step
+struct HmmLens { int lens[kNMax + 1]; int n; };
+
+template <bool LOG>
+__global__ void hmm_mstep_init_trans_kernel(HmmLens la, const double* __restrict__ initC,
+                                            const double* __restrict__ transC, double* __restrict__ accI,
+                                            double* __restrict__ accT, double* __restrict__ init,
+                                            double* __restrict__ trans) {
+  const int m = la.lens[blockIdx.x];
+  __shared__ double sC[kNMax * kNMax], sI[kNMax], sJ[2 * kNMax];
+  const int tid = threadIdx.x;
+  const double* ic = initC + (size_t)m * kNMax;
+  const double* tc = transC + (size_t)m * kNMax * kNMax;
+  double* io = init + (size_t)m * kNMax;
+  double* to = trans + (size_t)m * kNMax * kNMax;
+  if (LOG) {
+    double* ai = accI + (size_t)m * kNMax;
+    double* at = accT + (size_t)m * kNMax * kNMax;
+    for (int e = tid; e < m * m; e += blockDim.x) { at[e] = lse2(at[e], tc[e]); sC[e] = at[e]; }
+    for (int e = tid; e < m; e += blockDim.x) { ai[e] = lse2(ai[e], ic[e]); sI[e] = ai[e]; }
+    __syncthreads();
+    if (tid < m) {   // row r = tid: trans[r] -= LSE_s(acc[r][s])   (:364-369)
+      double mx = -INFINITY;
+      for (int c = 0; c < m; ++c) mx = fmax(mx, sC[tid * m + c]);
+      if (!(fabs(mx) < INFINITY)) mx = 0.0;
+      double s = 0.0;
+      for (int c = 0; c < m; ++c) s += exp(sC[tid * m + c] - mx);
+      const double nf = log(s) + mx;
+      for (int c = 0; c < m; ++c) to[tid * m + c] = sC[tid * m + c] - nf;
+    }
+    if (tid == 0) {  // init -= LSE(acc)   (:355-360)
+      double mx = -INFINITY;
+      for (int c = 0; c < m; ++c) mx = fmax(mx, sI[c]);
+      if (!(fabs(mx) < INFINITY)) mx = 0.0;
+      double s = 0.0;
+      for (int c = 0; c < m; ++c) s += exp(sI[c] - mx);
+      const double nf = log(s) + mx;
+      for (int c = 0; c < m; ++c) io[c] = sI[c] - nf;
+    }
+  } else {
+    for (int e = tid; e < m * m; e += blockDim.x) sC[e] = tc[e];
+    __syncthreads();
+    // Toeplitz pooling (:165-177), linear so applied to the summed counts
+    for (int dlt = tid; dlt < 2 * m - 1; dlt += blockDim.x) {
+      int offd = dlt - (m - 1);
+      double s = 0.0;
+      for (int r = 0; r < m; ++r) {
+        int c = r + offd;
+        if (c >= 0 && c < m) s += sC[r * m + c];
+      }
+      sJ[dlt] = s;
+    }
+    __syncthreads();
+    if (tid < m) {
+      double tot = 0.0;
+      for (int c = 0; c < m; ++c) tot += sJ[c - tid + m - 1];
+      if (tot != 0.0)
+        for (int c = 0; c < m; ++c) to[tid * m + c] = sJ[c - tid + m - 1] / tot;   // :279-286
+    }
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int c = 0; c < m; ++c) tot += ic[c];
+      for (int c = 0; c < m; ++c) io[c] = ic[c] / tot;                             // :276-277
+    }
+  }
+}
+
+// one warp per concept row: obs[tw][fw] = c / sum_fw c  (present entries only)
+template <bool LOG>
+__global__ void hmm_mstep_obs_kernel(const double* __restrict__ obsC, double* __restrict__ accO, int Vt,
+                                     int Vf, double* __restrict__ obs) {
+  const int tw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tw >= Vt) return;
+  const size_t base = (size_t)tw * Vf;
+  if (LOG) {
+    double m = -INFINITY;
+    for (int fw = lane; fw < Vf; fw += 32) {
+      double o = obs[base + fw];
+      if (o == o) {
+        double v = lse2(accO[base + fw], obsC[base + fw]);
+        accO[base + fw] = v;
+        m = fmax(m, v);
+      }
+    }
+    m = warp_max(m);
+    if (!(fabs(m) < INFINITY)) m = 0.0;
+    double s = 0.0;
+    for (int fw = lane; fw < Vf; fw += 32)
+      if (obs[base + fw] == obs[base + fw]) s += exp(accO[base + fw] - m);
+    s = warp_sum(s);
+    const double nf = log(s) + m;
+    for (int fw = lane; fw < Vf; fw += 32)
+      if (obs[base + fw] == obs[base + fw]) obs[base + fw] = accO[base + fw] - nf;   // :388-389
+  } else {
+    double s = 0.0;
+    for (int fw = lane; fw < Vf; fw += 32)
+      if (obs[base + fw] == obs[base + fw]) s += obsC[base + fw];
+    s = warp_sum(s);
+    for (int fw = lane; fw < Vf; fw += 32)
+      if (obs[base + fw] == obs[base + fw]) obs[base + fw] = obsC[base + fw] / s;    // :288-296
+  }
+}
+
+// ---------------------------------------------------------------- align
+struct HmmAlignArgs {
+  const int32_t* tgt_off;
+  const int32_t* tgt;
+  const int32_t* src_off;
+  const int32_t* src;
+  const double* init;
+  const double* trans;
+  const double* obs;
+  int32_t* alignment;
+  double* align_probs;
+  const int64_t* ap_off;
+  int64_t n_pairs;
+  int Vf, Tmax, warps_per_cta;
+  double unk;
+};
+
+__device__ __forceinline__ bool np_greater_h(double cand, double best) {
+  return (cand > best) || (cand != cand && best == best);
+}
+
+template <bool LOG>
+__global__ void __launch_bounds__(256) hmm_align_kernel(const HmmAlignArgs a) {
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int64_t pair = (int64_t)blockIdx.x * a.warps_per_cta + wic;
+  if (wic >= a.warps_per_cta || pair >= a.n_pairs) return;
+  extern __shared__ double smem[];
+  const size_t per_warp = 2 * kNMax * sizeof(double) + (size_t)a.Tmax * kNMax;
+  unsigned char* base = reinterpret_cast<unsigned char*>(smem) + (size_t)wic * ((per_warp + 7) / 8 * 8);
+  double* s_sc = reinterpret_cast<double*>(base);           // [2][NMAX]
+  unsigned char* s_bp = base + 2 * kNMax * sizeof(double);  // [Tmax][NMAX]
+  const int e0 = a.tgt_off[pair];
+  const int n = a.tgt_off[pair + 1] - e0;
+  const int f0 = a.src_off[pair];
+  const int T = a.src_off[pair + 1] - f0;
+  const int32_t* f = a.src + f0;
+  const int j = lane;
+  const bool on = j < n;
+  const double* A = a.trans + (size_t)n * MWD_TRANS_STRIDE;
+  const double* pi = a.init + (size_t)n * MWD_INIT_STRIDE;
+  const double* orow = a.obs + (size_t)(on ? a.tgt[e0 + j] : 0) * a.Vf;
+  double* ap = a.align_probs ? a.align_probs + a.ap_off[pair] : nullptr;
+  double sc = 0.0;
+  if (on) {
+    double b0 = orow[f[0]];
+    sc = LOG ? pi[j] + b0 : pi[j] * b0;                       // :307 / :402
+    s_sc[j] = sc;
+  }
+  __syncwarp();
+  for (int t = 1; t < T; ++t) {
+    const double* prev = s_sc + ((t - 1) & 1) * kNMax;
+    double* next = s_sc + (t & 1) * kNMax;
+    if (on) {
+      double b = orow[f[t]];
+      if (b != b) b = a.unk;                                  // :311 / :407
+      double best = LOG ? __dadd_rn(__dadd_rn(prev[0], A[j]), b) : __dmul_rn(__dmul_rn(prev[0], A[j]), b);
+      int arg = 0;
+      for (int i = 1; i < n; ++i) {
+        double cand = LOG ? __dadd_rn(__dadd_rn(prev[i], A[i * n + j]), b)
+                          : __dmul_rn(__dmul_rn(prev[i], A[i * n + j]), b);
+        if (np_greater_h(cand, best)) { best = cand; arg = i; }
+      }
+      s_bp[t * kNMax + j] = (unsigned char)arg;
+      sc = best;
+      next[j] = sc;
+    }
+    __syncwarp();
+    if (ap && on) {
+      if (LOG) {
+        ap[(size_t)(t - 1) * n + j] = sc;                     // :414
+      } else {
+        double tot = 0.0;
+        for (int i = 0; i < n; ++i) tot += next[i];
+        ap[(size_t)(t - 1) * n + j] = sc / tot;               // :316
+      }
+    }
+  }
+  if (lane == 0) {
+    const double* fin = s_sc + ((T - 1) & 1) * kNMax;
+    double best = fin[0];
+    int cur = 0;
+    for (int i = 1; i < n; ++i)
+      if (np_greater_h(fin[i], best)) { best = fin[i]; cur = i; }
+    a.alignment[f0 + T - 1] = cur;
+    for (int t = T - 1; t > 0; --t) {
+      cur = s_bp[t * kNMax + cur];
+      a.alignment[f0 + t - 1] = cur;
+    }
+  }
+}
+
+int sum_doubles(const double* x, int64_t n, double* blk_scratch, double* out, cudaStream_t st);
+
+}  // namespace mwd
+
+using namespace mwd;
+
+extern "C" int mwd_hmm_warps(void) { return hmm_warps_total(); }
+
+extern "C" int64_t mwd_hmm_counts_len(int Vt, int Vf) {
+  return (int64_t)Vt * Vf + (int64_t)(kNMax + 1) * kNMax + (int64_t)(kNMax + 1) * kNMax * kNMax + 1;
+}
+
+extern "C" int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  const int total = hmm_warps_total();
+  for (int b = 0; b < p->n_buckets; ++b) {
+    const int n = p->bucket_n[b];
+    const int64_t lo = p->bucket_lo[b], hi = p->bucket_lo[b + 1];
+    if (hi <= lo) continue;
+    MWD_REQUIRE(n >= 1 && n <= kNMax, "bucket %d: %d states outside [1,%d]", b, n, kNMax);
+    const int Tmax = p->bucket_tmax[b];
+    const size_t fixed = (size_t)(kNMax * kNMax + kNMax) * sizeof(double);
+    const size_t per_warp = ((size_t)Tmax * n + kNMax + kNMax * kNMax) * sizeof(double);
+    int wpc = (int)((220 * 1024 - fixed) / per_warp);
+    if (wpc > 8) wpc = 8;
+    MWD_REQUIRE(wpc >= 1, "caption of %d tokens x %d states does not fit in shared memory", Tmax, n);
+    // keep the warp count (rows of the partial tables) fixed: grid * wpc == total
+    while (total % wpc) --wpc;
+    const int grid = total / wpc;
+    HmmArgs a;
+    a.tgt_off = p->tgt_off; a.tgt = p->tgt; a.src_off = p->src_off; a.src = p->src;
+    a.slot_off = p->slot_off;
+    a.init = p->init + (size_t)n * MWD_INIT_STRIDE;
+    a.trans = p->trans + (size_t)n * MWD_TRANS_STRIDE;
+    a.obs = p->obs;
+    a.pair_ll = p->pair_ll; a.post = p->post;
+    a.part_init = p->part_init; a.part_trans = p->part_trans;
+    a.alpha_out = p->alpha_out; a.beta_out = p->beta_out;
+    a.lo = lo; a.hi = hi; a.n = n; a.Vf = p->n_src_types; a.Tmax = Tmax;
+    a.warps_per_cta = wpc; a.total_warps = total;
+    const size_t smem = fixed + (size_t)wpc * per_warp;
+    if (p->log_domain) {
+      MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_estep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hmm_estep_kernel<true><<<grid, wpc * 32, smem, st>>>(a);
+    } else {
+      MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_estep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hmm_estep_kernel<false><<<grid, wpc * 32, smem, st>>>(a);
+    }
+    MWD_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int mwd_hmm_reduce(const mwd_hmm_problem* p, const int64_t* post_idx, const int64_t* post_off,
+                              double* counts, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  const int rows = hmm_warps_total();
+  const int64_t oe = (int64_t)p->n_tgt_types * p->n_src_types;
+  const int64_t ie = (int64_t)(kNMax + 1) * kNMax;
+  const int64_t te = (int64_t)(kNMax + 1) * kNMax * kNMax;
+  const unsigned og = (unsigned)((oe + 7) / 8);
+  if (p->log_domain) {
+    hmm_postings_kernel<true><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
+    hmm_reduce_rows_kernel<true><<<(unsigned)((ie + 255) / 256), 256, 0, st>>>(p->part_init, rows, ie, counts + oe);
+    hmm_reduce_rows_kernel<true><<<(unsigned)((te + 255) / 256), 256, 0, st>>>(p->part_trans, rows, te, counts + oe + ie);
+  } else {
+    hmm_postings_kernel<false><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
+    hmm_reduce_rows_kernel<false><<<(unsigned)((ie + 255) / 256), 256, 0, st>>>(p->part_init, rows, ie, counts + oe);
+    hmm_reduce_rows_kernel<false><<<(unsigned)((te + 255) / 256), 256, 0, st>>>(p->part_trans, rows, te, counts + oe + ie);
+  }
+  MWD_CHECK_LAUNCH();
+  // log-likelihood sum; stage-1 partials parked in the (already consumed) head of part_trans
+  return sum_doubles(p->pair_ll, p->n_pairs, p->part_trans, counts + oe + ie + te, st);
+}
+
+extern "C" int mwd_hmm_mstep(const mwd_hmm_mstep_args* a, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  MWD_REQUIRE(a->n_lens >= 1 && a->n_lens <= kNMax, "n_lens %d outside [1,%d]", a->n_lens, kNMax);
+  HmmLens la;
+  la.n = a->n_lens;
+  for (int i = 0; i < a->n_lens; ++i) {
+    MWD_REQUIRE(a->lens[i] >= 1 && a->lens[i] <= kNMax, "length %d outside [1,%d]", a->lens[i], kNMax);
+    la.lens[i] = a->lens[i];
+  }
+  const int Vt = a->n_tgt_types, Vf = a->n_src_types;
+  const int64_t oe = (int64_t)Vt * Vf;
+  const int64_t ie = (int64_t)(kNMax + 1) * kNMax;
+  const double* obsC = a->counts;
+  const double* initC = a->counts + oe;
+  const double* transC = a->counts + oe + ie;
+  if (a->log_domain) {
+    MWD_REQUIRE(a->acc != nullptr, "log-domain M-step needs the running accumulators");
+    hmm_mstep_init_trans_kernel<true><<<a->n_lens, 64, 0, st>>>(la, initC, transC, a->acc + oe, a->acc + oe + ie,
+                                                             a->init, a->trans);
+    hmm_mstep_obs_kernel<true><<<(Vt + 7) / 8, 256, 0, st>>>(obsC, a->acc, Vt, Vf, a->obs);
+  } else {
+    hmm_mstep_init_trans_kernel<false><<<a->n_lens, 64, 0, st>>>(la, initC, transC, nullptr, nullptr, a->init,
+                                                              a->trans);
+    hmm_mstep_obs_kernel<false><<<(Vt + 7) / 8, 256, 0, st>>>(obsC, nullptr, Vt, Vf, a->obs);
+  }
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mwd_hmm_align(const mwd_hmm_problem* p, double unk_prob, int32_t* alignment,
+                             double* align_probs, const int64_t* ap_off, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  if (p->n_pairs <= 0) return 0;
+  MWD_REQUIRE(align_probs == nullptr || ap_off != nullptr, "align_probs needs ap_off");
+  HmmAlignArgs a;
+  a.tgt_off = p->tgt_off; a.tgt = p->tgt; a.src_off = p->src_off; a.src = p->src;
+  a.init = p->init; a.trans = p->trans; a.obs = p->obs;
+  a.alignment = alignment; a.align_probs = align_probs; a.ap_off = ap_off;
+  a.n_pairs = p->n_pairs; a.Vf = p->n_src_types; a.Tmax = p->t_max; a.unk = unk_prob;
+  size_t per_warp = 2 * kNMax * sizeof(double) + (size_t)a.Tmax * kNMax;
+  per_warp = (per_warp + 7) / 8 * 8;
+  int wpc = (int)((220 * 1024) / per_warp);
+  if (wpc > 8) wpc = 8;
+  MWD_REQUIRE(wpc >= 1, "caption of %d tokens does not fit in shared memory", a.Tmax);
+  a.warps_per_cta = wpc;
+  const size_t smem = per_warp * wpc;
+  const int64_t grid = (p->n_pairs + wpc - 1) / wpc;
+  MWD_REQUIRE(grid <= 0x7fffffff, "too many pairs for one launch");
+  if (p->log_domain) {
+    MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hmm_align_kernel<true><<<(unsigned)grid, wpc * 32, smem, st>>>(a);
+  } else {
+    MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hmm_align_kernel<false><<<(unsigned)grid, wpc * 32, smem, st>>>(a);
+  }
+  MWD_CHECK_LAUNCH();
+  return 0;
+}

@@ -103,7 +103,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     import ctypes as C
     lib = _lib.load()
-    for which, st in enumerate((_lib.Geometry, _lib.IkProblem, _lib.PartialSizes, _lib.IkMstepArgs)):
+    for which, st in enumerate((_lib.Geometry, _lib.IkProblem, _lib.PartialSizes, _lib.IkMstepArgs,
+                                _lib.HmmProblem, _lib.HmmMstepArgs)):
         assert lib.mwd_abi_sizeof(which) == C.sizeof(st)
 
 
