@@ -11,6 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import IkMstepArgs, IkProblem, MwdError, NMAX, PartialSizes
 from .corpus import dense_to_tables, tables_to_dense
+from .dist import fixed_order_allreduce
 
 
 def _ptr(t):
@@ -197,16 +198,7 @@ class IKEngine(object):
 
     def allreduce(self):
         """Sum [counts | grad] over ranks: all_gather + fixed-rank-order sum (bitwise reproducible)."""
-        torch = self.torch
-        dist = torch.distributed
-        if not (dist.is_available() and dist.is_initialized()):
-            return
-        world = dist.get_world_size(self.pg)
-        if world == 1:
-            return
-        gathered = torch.empty((world, self.reduced.numel()), dtype=self.reduced.dtype, device=self.device)
-        dist.all_gather_into_tensor(gathered, self.reduced, group=self.pg)
-        torch.sum(gathered, dim=0, out=self.reduced)
+        fixed_order_allreduce(self.reduced, self.pg)
 
     def mstep(self, lr, momentum, width=1.0):
         a = IkMstepArgs()

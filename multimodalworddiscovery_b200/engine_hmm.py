@@ -11,6 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import HmmMstepArgs, HmmProblem, MwdError, NMAX
 from .corpus import dense_to_tables, shard_positions, tables_to_dense
+from .dist import fixed_order_allreduce
 
 
 def _ptr(t):
@@ -177,19 +178,7 @@ class PlainHMMEngine(object):
                                            _ptr(self.counts), st))
 
     def allreduce(self):
-        torch = self.torch
-        dist = torch.distributed
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.pg) == 1:
-            return
-        world = dist.get_world_size(self.pg)
-        g = torch.empty((world, self.counts.numel()), dtype=self.counts.dtype, device=self.device)
-        dist.all_gather_into_tensor(g, self.counts, group=self.pg)
-        if self.log:
-            ll = g[:, -1].sum()
-            torch.logsumexp(g, dim=0, out=self.counts)
-            self.counts[-1] = ll
-        else:
-            torch.sum(g, dim=0, out=self.counts)
+        fixed_order_allreduce(self.counts, self.pg, log_domain=self.log, ll_index=self.counts_len - 1)
 
     def mstep(self):
         a = HmmMstepArgs()
