@@ -307,14 +307,11 @@ def gpu_arm(args):
         return eng.em_iteration(lr, mom, with_cA=False, timers=timers)
 
     def step_e2e():
-        # host -> device: the shard and the parameters; device -> host: LL + updated tables
-        eng.region_off.copy_(host['region_off'], non_blocking=True)
-        eng.phone_off.copy_(host['phone_off'], non_blocking=True)
-        eng.phones.copy_(host['phones'], non_blocking=True)
-        eng.feats.copy_(host['feats'], non_blocking=True)
+        # host -> device: the shard (streamed in chunks that overlap the kernels) and the
+        # parameters; device -> host: LL + updated tables
         for dst, src in zip((eng.init_t, eng.trans_t, eng.obsT, eng.post), h_params):
             dst.copy_(src, non_blocking=True)
-        ll = eng.em_iteration(lr, mom, with_cA=False)
+        ll = eng.em_iteration_streamed(host, lr, mom, n_chunks=args.chunks)
         h_ll.copy_(ll.reshape(1), non_blocking=True)
         for dst, src in zip(h_out, (eng.init_t, eng.trans_t, eng.obsT, eng.post)):
             dst.copy_(src, non_blocking=True)
@@ -395,7 +392,8 @@ def gpu_arm(args):
             'avg_log_likelihood': avg_ll,
             'e2e': {'value': args.pairs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
-            'gpu_launches': eng.kernel_launches_per_iteration() * args.steps * 2 * world,
+            'gpu_launches': (eng.kernel_launches_per_iteration() + eng.kernel_launches_per_iteration(args.chunks))
+                            * args.steps * world,
             'kernel_ms_per_step': kern_ms,
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': None,
@@ -420,6 +418,7 @@ def main():
     ap.add_argument('--variant', default='coco5', choices=['coco5', 'coco10'])
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--chunks', type=int, default=16, help='chunks of the streamed (e2e) iteration')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

@@ -148,6 +148,12 @@ int mwd_ik_reduce_counts(const mwd_ik_problem* p, double* counts, void* stream);
  * grad_partials [dev] : grad_splits x K x (D+1);  grad [dev] : K x (D+1).                    */
 int mwd_ik_posterior_grad(const mwd_ik_problem* p, double* grad_partials, double* grad,
                           void* stream);
+/* Streaming form for corpora processed in chunks (host-resident or larger than HBM): add one
+ * chunk's rows into the partials (accumulate = 0 for the first chunk), then reduce once.     */
+int mwd_ik_posterior_grad_partial(const mwd_ik_problem* p, double* grad_partials, int accumulate,
+                                  void* stream);
+int mwd_ik_posterior_grad_finish(int n_concepts, int feat_dim, const double* grad_partials,
+                                 double* grad, void* stream);
 
 /* M-step of trainUsingEM -- image_phone_hmm_word_discoverer.py:238-258 (gaussian :238-264).
  * Consumes the (globally reduced) `counts` and `grad`, updates init / trans / obsT and W or mus

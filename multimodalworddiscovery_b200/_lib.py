@@ -95,6 +95,8 @@ SYMBOLS = {
     'mwd_ik_counts_len': (_i64, [_i, _i]),
     'mwd_ik_reduce_counts': (_i, [C.POINTER(IkProblem), _vp, _vp]),
     'mwd_ik_posterior_grad': (_i, [C.POINTER(IkProblem), _vp, _vp, _vp]),
+    'mwd_ik_posterior_grad_partial': (_i, [C.POINTER(IkProblem), _vp, _i, _vp]),
+    'mwd_ik_posterior_grad_finish': (_i, [_i, _i, _vp, _vp, _vp]),
     'mwd_ik_mstep': (_i, [C.POINTER(IkMstepArgs), _vp]),
     'mwd_ik_decode': (_i, [C.POINTER(IkProblem), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'mwd_argmax_rows': (_i, [_vp, _i64, _i, _vp, _vp]),

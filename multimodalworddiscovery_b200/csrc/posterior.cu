@@ -217,7 +217,7 @@ template <int MT8, typename FT>
 __global__ void __launch_bounds__(256, (MT8 <= 9) ? 2 : 1)
 posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* __restrict__ cC,
                       const double* __restrict__ pz, int K, int64_t rows_per_split,
-                      double* __restrict__ partial) {
+                      double* __restrict__ partial, int accumulate) {
   constexpr int KP = 8 * MT8;
   constexpr int LDD = KP + 4;            // Delta tile [BR][KP], padded: 608 B == 96 mod 128 (KP=72)
   constexpr int LDV = BD + 4;            // V tile [BR][BD], padded: 1056 B == 32 mod 128
@@ -308,10 +308,16 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         int d = d0 + warp * 16 + j * 8 + l4 * 2 + h;
-        if (d < D) out[(size_t)k * ld + d] = acc[m][j][h];
+        if (d < D) {
+          double* o = out + (size_t)k * ld + d;
+          *o = accumulate ? (*o + acc[m][j][h]) : acc[m][j][h];
+        }
       }
   }
-  if (do_bias && tid < K) out[(size_t)tid * ld + D] = bias_acc;
+  if (do_bias && tid < K) {
+    double* o = out + (size_t)tid * ld + D;
+    *o = accumulate ? (*o + bias_acc) : bias_acc;
+  }
 }
 
 __global__ void grad_reduce_kernel(const double* __restrict__ partial, int splits, int64_t elems,
@@ -324,7 +330,7 @@ __global__ void grad_reduce_kernel(const double* __restrict__ partial, int split
 }
 
 template <int MT8>
-static int launch_grad(const mwd_ik_problem* p, double* partial, cudaStream_t st) {
+static int launch_grad(const mwd_ik_problem* p, double* partial, int accumulate, cudaStream_t st) {
   const int D = p->feat_dim, K = p->n_concepts;
   const int64_t R = p->n_regions;
   int64_t rps = (R + kGradSplits - 1) / kGradSplits;
@@ -333,10 +339,10 @@ static int launch_grad(const mwd_ik_problem* p, double* partial, cudaStream_t st
   dim3 grid((D + BD - 1) / BD, kGradSplits);
   if (p->feat_is_f64)
     posterior_grad_kernel<MT8, double><<<grid, 256, 0, st>>>((const double*)p->feats, R, D,
-                                                             p->concept_counts, p->pz, K, rps, partial);
+                                                             p->concept_counts, p->pz, K, rps, partial, accumulate);
   else
     posterior_grad_kernel<MT8, float><<<grid, 256, 0, st>>>((const float*)p->feats, R, D,
-                                                            p->concept_counts, p->pz, K, rps, partial);
+                                                            p->concept_counts, p->pz, K, rps, partial, accumulate);
   MWD_CHECK_LAUNCH();
   return 0;
 }
@@ -363,22 +369,37 @@ extern "C" int mwd_posterior_gaussian(const void* feats, int feat_is_f64, int64_
   return posterior_dispatch(feats, feat_is_f64, n_regions, feat_dim, w_scratch, n_concepts, pz, st);
 }
 
-extern "C" int mwd_ik_posterior_grad(const mwd_ik_problem* p, double* grad_partials, double* grad,
-                                     void* stream) {
-  cudaStream_t st = as_stream(stream);
+static int grad_partials_impl(const mwd_ik_problem* p, double* grad_partials, int accumulate,
+                              cudaStream_t st) {
   const int K = p->n_concepts;
   MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "n_concepts %d outside [1,%d]", K, MWD_KMAX);
   int rc = 2;
   switch ((K + 7) / 8) {
-#define MWD_MT(T) case T: rc = launch_grad<T>(p, grad_partials, st); break;
+#define MWD_MT(T) case T: rc = launch_grad<T>(p, grad_partials, accumulate, st); break;
     MWD_MT(1) MWD_MT(2) MWD_MT(3) MWD_MT(4) MWD_MT(5) MWD_MT(6) MWD_MT(7) MWD_MT(8)
     MWD_MT(9) MWD_MT(10) MWD_MT(11) MWD_MT(12) MWD_MT(13) MWD_MT(14) MWD_MT(15) MWD_MT(16)
 #undef MWD_MT
   }
-  if (rc) return rc;
-  const int64_t elems = (int64_t)K * (p->feat_dim + 1);
-  grad_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(grad_partials, kGradSplits,
-                                                                      elems, grad);
+  return rc;
+}
+
+extern "C" int mwd_ik_posterior_grad_partial(const mwd_ik_problem* p, double* grad_partials,
+                                             int accumulate, void* stream) {
+  return grad_partials_impl(p, grad_partials, accumulate, as_stream(stream));
+}
+
+extern "C" int mwd_ik_posterior_grad_finish(int n_concepts, int feat_dim, const double* grad_partials,
+                                            double* grad, void* stream) {
+  const int64_t elems = (int64_t)n_concepts * (feat_dim + 1);
+  grad_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, as_stream(stream)>>>(
+      grad_partials, kGradSplits, elems, grad);
   MWD_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int mwd_ik_posterior_grad(const mwd_ik_problem* p, double* grad_partials, double* grad,
+                                     void* stream) {
+  int rc = grad_partials_impl(p, grad_partials, 0, as_stream(stream));
+  if (rc) return rc;
+  return mwd_ik_posterior_grad_finish(p->n_concepts, p->feat_dim, grad_partials, grad, stream);
 }

@@ -190,11 +190,14 @@ class IKEngine(object):
         timed('posterior_grad', lambda: _lib.check(
             lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st)))
 
-    def kernel_launches_per_iteration(self):
-        """Kernels of libmwd_b200.so launched by one em_iteration (for bench.py's gpu_launches)."""
-        nb = int(np.count_nonzero(np.diff(self._bucket_lo) > 0))
+    def kernel_launches_per_iteration(self, n_chunks=None):
+        """Kernels of libmwd_b200.so launched by one em_iteration / em_iteration_streamed."""
         post = 2 if self.gaussian else 1
-        return post + nb + nb + 5 + 2 + 3
+        if n_chunks is None:
+            nb = int(np.count_nonzero(np.diff(self._bucket_lo) > 0))
+            return post + nb + nb + 5 + 2 + 3
+        per_chunk = sum(post + 2 * len(ch['bucket_n']) + 1 for ch in self.plan_chunks(n_chunks))
+        return per_chunk + 5 + 1 + 3
 
     def allreduce(self):
         """Sum [counts | grad] over ranks: all_gather + fixed-rank-order sum (bitwise reproducible)."""
@@ -217,6 +220,101 @@ class IKEngine(object):
         """One epoch body of trainUsingEM.  Returns the device scalar sum of log-likelihoods
         (over ALL ranks) of the parameters that entered the iteration."""
         self.estep(width, with_cA, timers)
+        self.allreduce()
+        ll = self.counts[self.counts_len - 1].clone()
+        self.mstep(lr, momentum, width)
+        return ll
+
+    # ------------------------------------------------------------------ streamed (host-resident) corpus
+    def plan_chunks(self, n_chunks):
+        """Contiguous chunks of the (n, T)-sorted shard with their own bucket descriptors."""
+        pk = self.pk
+        N = pk.n_pairs
+        n_chunks = max(1, min(int(n_chunks), N))
+        edges = np.linspace(0, N, n_chunks + 1).astype(np.int64)
+        chunks = []
+        for c in range(n_chunks):
+            lo, hi = int(edges[c]), int(edges[c + 1])
+            if hi <= lo:
+                continue
+            bn, blo, btm = [], [], []
+            for b in range(len(self._bucket_n)):
+                s, e = max(lo, int(self._bucket_lo[b])), min(hi, int(self._bucket_lo[b + 1]))
+                if e > s:
+                    bn.append(int(self._bucket_n[b]))
+                    blo.append(s - lo)
+                    btm.append(int(self._bucket_tmax[b]))
+            blo.append(hi - lo)
+            chunks.append(dict(lo=lo, hi=hi, r_lo=int(pk.region_off[lo]), r_hi=int(pk.region_off[hi]),
+                               p_lo=int(pk.phone_off[lo]), p_hi=int(pk.phone_off[hi]),
+                               bucket_n=np.array(bn, dtype=np.int32), bucket_lo=np.array(blo, dtype=np.int64),
+                               bucket_tmax=np.array(btm, dtype=np.int32)))
+        return chunks
+
+    def _chunk_problem(self, ch, for_grad=False):
+        p = self._problem(with_cA=False)
+        lo, hi, r_lo, r_hi = ch['lo'], ch['hi'], ch['r_lo'], ch['r_hi']
+        p.n_pairs = hi - lo
+        p.n_buckets = len(ch['bucket_n'])
+        p.bucket_n, p.bucket_lo = _np_ptr(ch['bucket_n']), _np_ptr(ch['bucket_lo'])
+        p.bucket_tmax = _np_ptr(ch['bucket_tmax'])
+        # offset arrays are shifted to the chunk's first pair; their VALUES stay absolute row / phone
+        # indices, so the per-region and per-phone arrays keep their base pointers
+        p.region_off = _ptr(self.region_off[lo:])
+        p.phone_off = _ptr(self.phone_off[lo:])
+        p.pair_ll = _ptr(self.pair_ll[lo:])
+        if for_grad:   # the gradient GEMM walks rows [0, n_regions) of the arrays it is given
+            p.n_regions = r_hi - r_lo
+            p.feats = _ptr(self.feats[r_lo:r_hi])
+            p.pz = _ptr(self.pz[r_lo:r_hi])
+            p.concept_counts = _ptr(self.cC[r_lo:r_hi])
+        return p
+
+    def em_iteration_streamed(self, host, lr, momentum, width=1.0, n_chunks=16):
+        """One EM iteration with the corpus streamed from (pinned) host memory: the copy of chunk
+        c+1 overlaps the kernels of chunk c.  ``host``: dict of pinned CPU tensors region_off,
+        phone_off, feats, phones laid out like the device buffers.  Same result as em_iteration
+        up to the association order of the chunked gradient partials."""
+        torch, lib = self.torch, self.lib
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, '_chunks', None) is None or len(self._chunks) != n_chunks:
+            self._chunks = self.plan_chunks(n_chunks)
+        chunks = self._chunks
+        cs.wait_stream(main)                       # previous iteration no longer reads the buffers
+        events = []
+        with torch.cuda.stream(cs):
+            self.region_off.copy_(host['region_off'], non_blocking=True)
+            self.phone_off.copy_(host['phone_off'], non_blocking=True)
+            for ch in chunks:
+                self.feats[ch['r_lo']:ch['r_hi']].copy_(host['feats'][ch['r_lo']:ch['r_hi']], non_blocking=True)
+                self.phones[ch['p_lo']:ch['p_hi']].copy_(host['phones'][ch['p_lo']:ch['p_hi']], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        st = self._stream()
+        self.part.zero_()
+        for c, (ch, ev) in enumerate(zip(chunks, events)):
+            main.wait_event(ev)
+            R = ch['r_hi'] - ch['r_lo']
+            f_ptr, pz_ptr = _ptr(self.feats[ch['r_lo']:ch['r_hi']]), _ptr(self.pz[ch['r_lo']:ch['r_hi']])
+            if self.gaussian:
+                _lib.check(lib.mwd_posterior_gaussian(f_ptr, self.feat_is_f64, R, self.D, _ptr(self.post),
+                                                      float(width), self.K, _ptr(self.w_scratch), pz_ptr, st))
+            else:
+                _lib.check(lib.mwd_posterior_linear(f_ptr, self.feat_is_f64, R, self.D, _ptr(self.post),
+                                                    self.K, pz_ptr, st))
+            prob = self._chunk_problem(ch)
+            _lib.check(lib.mwd_ik_estep(C.byref(prob), st))
+            _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st))
+            gprob = self._chunk_problem(ch, for_grad=True)
+            _lib.check(lib.mwd_ik_posterior_grad_partial(C.byref(gprob), _ptr(self.grad_partials),
+                                                         1 if c > 0 else 0, st))
+        full = self._problem(with_cA=False)
+        _lib.check(lib.mwd_ik_reduce_counts(C.byref(full), _ptr(self.counts), st))
+        _lib.check(lib.mwd_ik_posterior_grad_finish(self.K, self.D, _ptr(self.grad_partials), _ptr(self.grad), st))
         self.allreduce()
         ll = self.counts[self.counts_len - 1].clone()
         self.mstep(lr, momentum, width)

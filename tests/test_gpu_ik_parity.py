@@ -109,3 +109,27 @@ def test_em_matches_oracle_random(kind, K, P, D, nmax):
         np.testing.assert_allclose(post, p['W' if kind == 'linear' else 'mus'], rtol=1e-8, atol=1e-12)
         np.testing.assert_allclose(_unsort_rows(pk, eng.cC.cpu().numpy(), pk.region_off),
                                    np.concatenate(info['cC']), rtol=RTOL, atol=1e-300)
+
+
+@pytest.mark.parametrize('case', ['mixed_linear', 'mixed_gaussian', 'short_toeplitz_linear'])
+def test_streamed_iteration_equals_resident(case):
+    """em_iteration_streamed (chunked H2D overlapped with the kernels) == em_iteration."""
+    import torch
+    g = load_ik(case)
+    pk, eng = _engine_for(g, keep_cA=False)
+    _, eng2 = _engine_for(g, keep_cA=False)
+    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(pk, k))).pin_memory()
+            for k in ('region_off', 'phone_off', 'feats', 'phones')}
+    for it in range(2):
+        ll1 = float(eng.em_iteration(g['lr'], g['momentum'], g['width'], with_cA=False))
+        eng2.feats.zero_()      # prove the data really comes from the host copy
+        eng2.phones.zero_()
+        ll2 = float(eng2.em_iteration_streamed(host, g['lr'], g['momentum'], g['width'], n_chunks=5))
+        assert ll2 == pytest.approx(ll1, rel=1e-13)
+        for a, b in zip(eng.get_params(), eng2.get_params()):
+            if isinstance(a, dict):
+                for m in a:
+                    np.testing.assert_allclose(b[m], a[m], rtol=1e-12)
+            else:
+                np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose(eng2.cC.cpu().numpy(), eng.cC.cpu().numpy(), rtol=1e-12, atol=1e-300)
