@@ -63,25 +63,36 @@ __global__ void __launch_bounds__(1024) ik_concept_kernel(const ConceptArgs a) {
 
   const double* A = c_trans + N * (kNMax * kNMax);
   const double* pi = c_init + N * kNMax;
+  // one step of the restricted chain: G = (F A) * e', e'[j] = e_t[j] except e'[i] = o
+  auto chain_step = [&](const double (&F)[N], double (&G)[N], const double* et, double o, int i) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < N; ++l) acc = fma(F[l], A[l * N + j], acc);
+      G[j] = acc * ((j == i) ? o : et[j]);
+    }
+  };
   for (int c = tid; c < N * K; c += blockDim.x) {
     const int i = c / K, k = c - i * K;
-    double F[N];
+    const double* ocol = a.obsT + k;
+    double F[N], G[N];
     {
-      double o = __ldg(a.obsT + (size_t)s_x[0] * K + k);
+      double o = __ldg(ocol + (size_t)s_x[0] * K);
 #pragma unroll
       for (int j = 0; j < N; ++j) F[j] = pi[j] * ((j == i) ? o : s_e[j]);
     }
-    for (int t = 1; t < T; ++t) {
-      const double o = __ldg(a.obsT + (size_t)s_x[t] * K + k);
-      const double* et = s_e + t * N;
-      double G[N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        double acc = 0.0;
-#pragma unroll
-        for (int l = 0; l < N; ++l) acc = fma(F[l], A[l * N + j], acc);
-        G[j] = acc * ((j == i) ? o : et[j]);
-      }
+    int t = 1;
+    // two steps per trip (F -> G -> F): no register copies between steps
+    for (; t + 1 < T; t += 2) {
+      const double o0 = __ldg(ocol + (size_t)s_x[t] * K);
+      const double o1 = __ldg(ocol + (size_t)s_x[t + 1] * K);
+      chain_step(F, G, s_e + t * N, o0, i);
+      chain_step(G, F, s_e + (t + 1) * N, o1, i);
+    }
+    if (t < T) {
+      const double o0 = __ldg(ocol + (size_t)s_x[t] * K);
+      chain_step(F, G, s_e + t * N, o0, i);
 #pragma unroll
       for (int j = 0; j < N; ++j) F[j] = G[j];
     }

@@ -243,7 +243,7 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
   constexpr int DPT = (BR * KP + 255) / 256;
   // V tile: BR*BD elements, thread handles column tid & 127, rows (tid >> 7) + 2 q
   constexpr int VPT = BR / 2;
-  double dreg[DPT];
+  double creg[DPT], preg[DPT];   // raw cC / pz; subtracted only at staging time
   FT vreg[VPT];
   const int vcol = tid & 127, vrow = tid >> 7;
   const bool vcol_ok = d0 + vcol < D;
@@ -254,7 +254,9 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
       int e = tid + 256 * q;
       int rr = e / KP, k = e - rr * KP;
       int64_t r = r0 + rr;
-      dreg[q] = (e < BR * KP && r < rend && k < K) ? (__ldg(cC + r * K + k) - __ldg(pz + r * K + k)) : 0.0;
+      const bool ok = (e < BR * KP && r < rend && k < K);
+      creg[q] = ok ? __ldg(cC + r * K + k) : 0.0;
+      preg[q] = ok ? __ldg(pz + r * K + k) : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < VPT; ++q) {
@@ -267,7 +269,7 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
     for (int q = 0; q < DPT; ++q) {
       int e = tid + 256 * q;
       int rr = e / KP, k = e - rr * KP;
-      if (e < BR * KP) sDl[rr * LDD + k] = dreg[q];
+      if (e < BR * KP) sDl[rr * LDD + k] = creg[q] - preg[q];
     }
 #pragma unroll
     for (int q = 0; q < VPT; ++q) sV[(vrow + 2 * q) * LDV + vcol] = (double)vreg[q];
