@@ -96,6 +96,10 @@ typedef struct {
   double* part_trans;        /* [dev] estep_grid x (MWD_NMAX+1) x MWD_NMAX*MWD_NMAX         */
   double* scratch;           /* [dev] checkpoint scratch, scratch_bytes long                */
   int64_t scratch_bytes;
+  double* stats;             /* [dev] 4 * slot_off[N] doubles: per (pair, t) row statistics
+                                (s_t, floor-sum, xi diagonal, r_t; n each) handed from the
+                                recursion kernel to the count post-pass                      */
+  const int64_t* slot_off;   /* [dev] N+1: slot_off[p] = sum_{q<p} T_q * n_q                */
 } mwd_ik_problem;
 
 /* bytes of `scratch` mwd_ik_estep needs for this problem (depends on t_max, bucket_n, K) */

@@ -15,7 +15,11 @@
 //     recomputes the B-1 slices in between into shared memory (barrier-free: the coupling terms
 //     c_t were stored on the way forward), so no (T,n,K) tensor ever reaches HBM;
 //   * everything stays in the raw float64 probability domain with the reference's EPS floors.
-//   * counts are accumulated without atomics: init/trans in registers of fixed threads, phone
+//   * the recursion kernel only publishes per-step row statistics (s_t, floor-sum, xi diagonal,
+//     r_t: 4n doubles per step); the init / transition count bookkeeping (EPS floors, per-step
+//     normalisers) runs in a separate, fully parallel post-pass kernel (ik_counts_kernel), so it
+//     never sits on the recursion's critical path;
+//   * counts are accumulated without atomics: init/trans in registers of fixed warps, phone
 //     counts by read-modify-write of a per-CTA table that only this CTA touches, in t order.
 #include "mwd_common.cuh"
 
@@ -35,14 +39,17 @@ struct EstepArgs {
   double* part_init;     // [grid][(NMAX+1)*NMAX]
   double* part_trans;    // [grid][(NMAX+1)*NMAX*NMAX]
   double* scratch;
+  double* stats;         // [slot_off[N]][4]: per (pair, t): s_t[n], floor-sum[n], xi-diag[n], r_t[n]
+  const int64_t* slot_off;
   int64_t lo, hi;
   int64_t cta_scratch;   // doubles per CTA
   int n, K, P, B, NC, Tmax;
   int ll_only;           // 1: forward sweep + log-likelihood only
 };
 
-constexpr int NQ = 5;  // exchanged per-row quantities: floor-sum, g-sum, diag, r, xi-row-sum
+constexpr int NQ = 1;   // exchanged per-row quantity: s_t (forward) / r_t (backward)
 constexpr int BMAX = 8; // max checkpoint interval
+constexpr int kEPP = 4; // pairs per CTA
 
 // phone-count table update for one column k and the PP rows deferred by the previous step.
 // All loads are issued first; equal phone ids are forwarded so the result equals the sequential
@@ -65,13 +72,17 @@ __device__ __forceinline__ void drain_column(double* tab, int K, int k, const in
     if (xs[s] >= 0) tab[xs[s] * K + k] = v[s];
 }
 
+constexpr int estep_min_blocks(int nn) { return nn <= 0 ? 1 : (480 / (32 * nn) < 1 ? 1 : 480 / (32 * nn)); }
+
 // KG = ceil(K/8) exactly: only the last of a lane's KG concepts can fall outside [0,K).
-// NJ = ceil(n/8): xi columns per lane.
-template <int KG, int NJ, int PP, bool TAB>
-__global__ void __launch_bounds__(PP * 8 * 8 * NJ, NJ == 1 ? 2 : 1)
+// NN > 0: n is a compile-time constant (index math folds, the n-loops unroll); NN == 0: generic.
+template <int KG, int NN, bool TAB>
+__global__ void __launch_bounds__(NN > 0 ? 32 * NN : 512, estep_min_blocks(NN))
 ik_estep_kernel(const EstepArgs a) {
+  constexpr int PP = kEPP;
   constexpr int KS = KG * kLanesPerRow;
-  const int n = a.n, K = a.K, B = a.B;
+  const int n = (NN > 0) ? NN : a.n;
+  const int K = a.K, B = a.B;
   const int tid = threadIdx.x;
   const int l8 = tid & 7;
   const int grp = tid >> 3;
@@ -82,16 +93,18 @@ ik_estep_kernel(const EstepArgs a) {
 
   extern __shared__ double smem[];
   // shared-memory map (offsets in doubles)
-  const int o_exch = PP * B * n * KS;                     // [2][PP][NQ][NMAX]
-  const int o_aoff = o_exch + 2 * PP * NQ * kNMax;        // [n][n]
+  const int o_exch = PP * B * n * KS;                     // [2][PP][NMAX]
+  const int o_aoff = o_exch + 2 * PP * kNMax;             // [n][n]
   const int o_d = o_aoff + kNMax * kNMax;                 // [n]
   const int o_pi = o_d + kNMax;                           // [n]
-  const int o_cA = o_pi + kNMax;                          // [2][PP][K]
+  const int o_in = o_pi + kNMax;                          // [PP]  1 / max(L, EPS)
+  const int o_cA = o_in + PP;                             // [2][PP][K]
   const int o_tab = o_cA + 2 * PP * K;                    // [P][K]   (TAB)
   const int o_x = o_tab + (TAB ? a.P * K : 0);            // ints: [PP][TX]
   double* s_buf = smem;
   double* s_exch = smem + o_exch;
   double* s_aoff = smem + o_aoff;
+  double* s_inorm = smem + o_in;
   double* s_cA = smem + o_cA;
   int* s_x = reinterpret_cast<int*>(smem + o_x);
   __shared__ int s_T[PP];
@@ -110,7 +123,7 @@ ik_estep_kernel(const EstepArgs a) {
 
   double* cta_scr = a.scratch + (size_t)blockIdx.x * a.cta_scratch;
   double* my_ckpt = cta_scr + ((size_t)slot * a.NC * n + i) * KS + l8;              // + c*n*KS + 8j
-  double* my_hist = cta_scr + (size_t)PP * a.NC * n * KS + (size_t)slot * a.Tmax * 2 * n + i;  // + (t*2+w)*n
+  double* my_hist = cta_scr + (size_t)PP * a.NC * n * KS + (size_t)slot * a.Tmax * n + i;  // + t*n : c_t[i]
   const int buf_row = (slot * B * n + i) * KS + l8;                                  // + tt*n*KS + 8j
   const int nKS = n * KS;
   double* g_phone = a.part_phone + (size_t)blockIdx.x * a.P * K;
@@ -118,27 +131,28 @@ ik_estep_kernel(const EstepArgs a) {
   const int* my_x = s_x + slot * TX;
   const double* obsT = a.obsT + l8;
 
-  // persistent accumulators
-  double init_acc = 0.0;          // lane 0 of each row: sum_t floor-sum_i / total
-  double trans_acc[NJ];           // lane l of row i: xi[i][l + 8*jj]
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) trans_acc[jj] = 0.0;
-
   const int64_t npairs = a.hi - a.lo;
   const int64_t nquads = (npairs + PP - 1) / PP;
   __syncthreads();
   const double d_i = smem[o_d + i];
   const double pi_i = smem[o_pi + i];
+  double aoff_row[NN > 0 ? NN : 1];     // Aoff[i][:] in registers when n is static
+  if (NN > 0) {
+#pragma unroll
+    for (int j = 0; j < NN; ++j) aoff_row[j] = s_aoff[i * n + j];
+  }
 
   for (int64_t quad = blockIdx.x; quad < nquads; quad += gridDim.x) {
     const int64_t pair = a.lo + quad * PP + slot;
     const bool valid = pair < a.hi;
     int T = 0;
     int64_t r0 = 0, p0 = 0;
+    double* my_stats = a.stats;
     if (valid) {
       p0 = a.phone_off[pair];
       T = a.phone_off[pair + 1] - (int32_t)p0;
       r0 = a.region_off[pair];
+      my_stats = a.stats + 4 * a.slot_off[pair] + i;      // + (t*4 + q)*n
     }
     __syncthreads();  // previous quad fully done (exchange + buffers reusable)
     if (i == 0 && l8 == 0) {
@@ -191,7 +205,7 @@ ik_estep_kernel(const EstepArgs a) {
         for (int j = 0; j < KG; ++j) s += al[j];
       }
       s = row8_sum(s);
-      const int exo = ((par * PP + slot) * NQ) * kNMax;
+      const int exo = (par * PP + slot) * kNMax;
       if (l8 == 0) s_exch[exo + i] = s;
       __syncthreads();
       if (act) {
@@ -200,14 +214,20 @@ ik_estep_kernel(const EstepArgs a) {
           if (i == 0 && l8 == 0) {
             double L = 0.0;
             for (int j = 0; j < n; ++j) L += ex[j];
-            a.pair_ll[pair] = log(floor_eps(L));
+            L = floor_eps(L);
+            a.pair_ll[pair] = log(L);                              // :529
+            // sum_{i,k} alpha_t beta_t equals the sentence likelihood at every t, so the floored
+            // normaliser of updateStateCounts (:430) is one constant per pair
+            s_inorm[slot] = 1.0 / L;
           }
         } else {
           double c = 0.0;
-          for (int j = 0; j < n; ++j) c = fma(s_aoff[j * n + i], ex[j], c);
+#pragma unroll
+          for (int j = 0; j < (NN > 0 ? NN : kNMax); ++j)
+            if (NN > 0 || j < n) c = fma(s_aoff[j * n + i], ex[j], c);
           if (l8 == 0 && !a.ll_only) {
-            __stcg(my_hist + (t * 2 + 0) * n, c);
-            __stcg(my_hist + (t * 2 + 1) * n, s);
+            __stcg(my_hist + t * n, c);
+            __stcg(my_stats + (t * 4 + 0) * n, s);
           }
 #pragma unroll
           for (int j = 0; j < KG; ++j) al[j] = onext[j] * fma(d_i, al[j], c * pz[j]);
@@ -222,13 +242,6 @@ ik_estep_kernel(const EstepArgs a) {
 #pragma unroll
     for (int j = 0; j < KG; ++j) bo[j] = 0.0;
     double w = 0.0;         // (Aoff r_{t+1})[i]
-    double r_next[NJ];      // r_{t+1}[j] for this lane's xi columns
-    double x_hold[NJ];      // floored xi_t[i][j] waiting for its normaliser
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) { r_next[jj] = 0.0; x_hold[jj] = 0.0; }
-    bool pend = false;
-    double zrow = 0.0;
-    double s_pref = 0.0;    // s_t[i] prefetched one step ahead
     int step = 0;           // parity counter of the exchange buffers
 
     const int nblk = (Tmax + B - 1) / B;
@@ -241,7 +254,7 @@ ik_estep_kernel(const EstepArgs a) {
         double cb[BMAX];
 #pragma unroll
         for (int tt = 1; tt < BMAX; ++tt)
-          cb[tt] = (tt < len && t0 + tt < T) ? __ldcg(my_hist + ((t0 + tt - 1) * 2 + 0) * n) : 0.0;
+          cb[tt] = (tt < len && t0 + tt < T) ? __ldcg(my_hist + (t0 + tt - 1) * n) : 0.0;
 #pragma unroll
         for (int j = 0; j < KG; ++j) {
           al[j] = __ldcg(src + 8 * j);
@@ -265,9 +278,7 @@ ik_estep_kernel(const EstepArgs a) {
         const int t = t0 + tt;
         const bool act = t < T;
         const int par = step & 1;
-        double sumF = 0.0, sumG = 0.0, dg = 0.0, rr = 0.0;
-        const double s_cur = s_pref;
-        if (t >= 1 && t - 1 < T - 1) s_pref = __ldcg(my_hist + ((t - 1) * 2 + 1) * n);
+        double sumF = 0.0, dg = 0.0, rr = 0.0;
         int x = 0;
         if (act) {
           x = my_x[t];
@@ -281,7 +292,6 @@ ik_estep_kernel(const EstepArgs a) {
             double beta = last ? 1.0 : fma(d_i, bo[j], w);
             dg = fma(av, bo[j], dg);
             double g = av * beta;
-            sumG += g;
             sumF += kv ? floor_eps(g) : 0.0;
             double o = kv ? __ldg(orow + 8 * j) : 0.0;
             bo[j] = beta * o;
@@ -291,19 +301,16 @@ ik_estep_kernel(const EstepArgs a) {
           dg *= d_i;
         }
         sumF = row8_sum(sumF);
-        sumG = row8_sum(sumG);
         dg = row8_sum(dg);
         rr = row8_sum(rr);
-        double zr = row8_sum(zrow);
-        zrow = 0.0;
-        const int exo = ((par * PP + slot) * NQ) * kNMax;
+        const int exo = (par * PP + slot) * kNMax;
         if (l8 == 0) {
-          double* ex = s_exch + exo + i;
-          ex[0 * kNMax] = sumF;
-          ex[1 * kNMax] = sumG;
-          ex[2 * kNMax] = dg;
-          ex[3 * kNMax] = rr;
-          ex[4 * kNMax] = zr;
+          s_exch[exo + i] = rr;
+          if (act) {   // row statistics of this step for the count post-pass
+            __stcg(my_stats + (t * 4 + 1) * n, sumF);
+            __stcg(my_stats + (t * 4 + 2) * n, dg);
+            __stcg(my_stats + (t * 4 + 3) * n, rr);
+          }
         }
         __syncthreads();
         // drain the phone-count rows deferred by the previous step: thread k owns column k of
@@ -314,48 +321,23 @@ ik_estep_kernel(const EstepArgs a) {
         if (i == 0 && l8 == 0) s_xs[par][slot] = act ? x : -1;
         if (act) {
           const double* ex = s_exch + exo;
-          double Ft = 0.0, Gt = 0.0, Zt = 0.0, wn = 0.0;
-          for (int j = 0; j < n; ++j) {
-            Ft += ex[0 * kNMax + j];
-            Gt += ex[1 * kNMax + j];
-            Zt += ex[4 * kNMax + j];
-            wn = fma(s_aoff[i * n + j], ex[3 * kNMax + j], wn);
-          }
-          if (l8 == 0) init_acc += sumF * __drcp_rn(Ft);         // :355
-          if (pend) {                                            // normalise xi_{t+1}  (:396)
-            const double iz = __drcp_rn(Zt);
+          double wn = 0.0;
+          if (NN > 0) {
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) trans_acc[jj] = fma(x_hold[jj], iz, trans_acc[jj]);
-            pend = false;
-          }
-          if (t < T - 1) {                                       // xi_t  (:388-389)
-            zrow = 0.0;
-#pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) {
-              int j = l8 + 8 * jj;
-              double xv = 0.0;
-              if (j < n) {
-                double xi = (j == i) ? ex[2 * kNMax + i] : (s_cur * s_aoff[i * n + j]) * r_next[jj];
-                xv = floor_eps(xi);
-              }
-              x_hold[jj] = xv;
-              zrow += xv;
-            }
-            pend = true;
-          }
-#pragma unroll
-          for (int jj = 0; jj < NJ; ++jj) {
-            int j = l8 + 8 * jj;
-            r_next[jj] = (j < n) ? ex[3 * kNMax + j] : 0.0;
+            for (int j = 0; j < (NN > 0 ? NN : 1); ++j) wn = fma(aoff_row[j], ex[j], wn);
+          } else {
+            for (int j = 0; j < n; ++j) wn = fma(s_aoff[i * n + j], ex[j], wn);
           }
           w = wn;
           // conceptCountsA[t][k] = sum_i gamma_t[i][k]; phoneCounts[k][x_t] += ...  (:430,:233,:235)
-          const double inorm = __drcp_rn(floor_eps(Gt));
+          const double inorm = s_inorm[slot];
           const double* col = s_buf + (slot * B + tt) * nKS;
           double* crow = s_cA + (par * PP + slot) * K;
           for (int k = i * kLanesPerRow + l8; k < K; k += n * kLanesPerRow) {
             double v = 0.0;
-            for (int ii = 0; ii < n; ++ii) v += col[ii * KS + k];
+#pragma unroll
+            for (int ii = 0; ii < (NN > 0 ? NN : kNMax); ++ii)
+              if (NN > 0 || ii < n) v += col[ii * KS + k];
             v *= inorm;
             crow[k] = v;
             if (a.cA_out) a.cA_out[(p0 + t) * K + k] = v;
@@ -363,53 +345,193 @@ ik_estep_kernel(const EstepArgs a) {
         }
       }
     }
-    // flush the last pending xi normaliser (xi_0) and the last deferred phone-count rows
+    // flush the last deferred phone-count rows
     {
       const int par = step & 1;
-      double zr = row8_sum(zrow);
-      zrow = 0.0;
-      const int exo = ((par * PP + slot) * NQ + 4) * kNMax;
-      if (l8 == 0) s_exch[exo + i] = zr;
       __syncthreads();
       for (int k = tid; k < K; k += blockDim.x)
         drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
-      if (pend) {
-        const double* ex = s_exch + exo;
-        double Zt = 0.0;
-        for (int j = 0; j < n; ++j) Zt += ex[j];
-        const double iz = __drcp_rn(Zt);
-#pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) trans_acc[jj] = fma(x_hold[jj], iz, trans_acc[jj]);
-        pend = false;
-      }
     }
   }
 
   if (a.ll_only) return;
-  // ---------------------------------------------------------------- per-CTA partial tables
+  // ---------------------------------------------------------------- per-CTA phone-count table
   __syncthreads();
   if (TAB)
     for (int e = tid; e < a.P * K; e += blockDim.x) g_phone[e] += smem[o_tab + e];
-  double* red = s_buf;  // reuse: [PP][n][n] then [PP][n]
+}
+
+// ------------------------------------------------------------------------------------------
+// Count post-pass: updateInitialCounts (:347-362) and updateTransitionCounts (:374-416) from the
+// per-step row statistics.  One warp per pair (persistent, fixed pair->warp map), lanes own the
+// n x n transition entries; every time step is independent, so nothing here is latency-critical.
+// ------------------------------------------------------------------------------------------
+struct CountsArgs {
+  const int32_t* phone_off;
+  const double* trans;     // trans[n]
+  const double* stats;
+  const int64_t* slot_off;
+  double* part_init;
+  double* part_trans;
+  int64_t lo, hi;
+  int n, total_warps;
+};
+
+__device__ __forceinline__ double warp_sum_all(double v) {
 #pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) {
-    int j = l8 + 8 * jj;
-    if (j < n) red[(slot * n + i) * n + j] = trans_acc[jj];
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) ik_counts_kernel(const CountsArgs a) {
+  constexpr int EPL = (kNMax * kNMax + 31) / 32;   // transition entries per lane (8)
+  const int n = a.n;
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nn = n * n;
+  const int epl = (nn + 31) >> 5;                  // entries per lane actually used
+  // per-lane constants of its entries e = lane + 32 q -> (r, c): offsets into the stats rows
+  int off_a[EPL], off_b[EPL];                      // xi = stats[off_a] * coef * next[off_b] (off-diag)
+  double coef[EPL];                                //      stats[off_a]                      (diag: coef < 0)
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    const int e = lane + 32 * q;
+    off_a[q] = 0; off_b[q] = 0; coef[q] = 0.0;
+    if (e < nn) {
+      const int r = e / n, c = e - r * n;
+      if (r == c) { off_a[q] = 2 * n + r; coef[q] = -1.0; }
+      else { off_a[q] = r; off_b[q] = 3 * n + c; coef[q] = a.trans[e]; }
+    }
   }
-  double* red_i = red + PP * n * n;
-  if (l8 == 0) red_i[slot * n + i] = init_acc;
+  double acc_t[EPL];
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) acc_t[q] = 0.0;
+  double acc_i = 0.0;
+  for (int64_t pair = a.lo + gw; pair < a.hi; pair += a.total_warps) {
+    const int T = a.phone_off[pair + 1] - a.phone_off[pair];
+    const double* st = a.stats + 4 * a.slot_off[pair];
+    for (int t = 0; t < T; ++t) {
+      const double* row = st + (size_t)t * 4 * n;
+      // updateInitialCounts: sum_k max(g,EPS) per region over its total (:355)
+      const double f = (lane < n) ? __ldcg(row + n + lane) : 0.0;
+      double xv[EPL];
+      double z = 0.0;
+      if (t < T - 1) {
+        // xi_t = diag(d o beta alpha) + s_t Aoff r_{t+1}, EPS-floored, normalised (:388-396)
+        const double* nxt = row + 4 * n;
+#pragma unroll
+        for (int q = 0; q < EPL; ++q) {
+          xv[q] = 0.0;
+          if (q < epl && lane + 32 * q < nn) {
+            const double u = __ldcg(row + off_a[q]);
+            const double xi = (coef[q] < 0.0) ? u : (u * coef[q]) * __ldcg(nxt + off_b[q]);
+            xv[q] = floor_eps(xi);
+            z += xv[q];
+          }
+        }
+      }
+      const double Ft = warp_sum_all(f);
+      acc_i += f / Ft;
+      if (t < T - 1) {
+        const double iz = 1.0 / warp_sum_all(z);
+#pragma unroll
+        for (int q = 0; q < EPL; ++q)
+          if (q < epl) acc_t[q] = fma(xv[q], iz, acc_t[q]);
+      }
+    }
+  }
+  // combine the CTA's 8 warps in fixed order, then add into this CTA's partial row
+  __shared__ double s_red[8][kNMax * kNMax + kNMax];
+  const int wic = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    const int e = lane + 32 * q;
+    if (e < nn) s_red[wic][e] = acc_t[q];
+  }
+  if (lane < n) s_red[wic][kNMax * kNMax + lane] = acc_i;
   __syncthreads();
   double* pt = a.part_trans + ((size_t)blockIdx.x * (kNMax + 1) + n) * (kNMax * kNMax);
   double* pi_out = a.part_init + ((size_t)blockIdx.x * (kNMax + 1) + n) * kNMax;
-  for (int e = tid; e < n * n; e += blockDim.x) {
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     double v = 0.0;
-    for (int s = 0; s < PP; ++s) v += red[s * n * n + e];
+    for (int w2 = 0; w2 < 8; ++w2) v += s_red[w2][e];
     pt[e] += v;
   }
-  for (int e = tid; e < n; e += blockDim.x) {
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
     double v = 0.0;
-    for (int s = 0; s < PP; ++s) v += red_i[s * n + e];
+    for (int w2 = 0; w2 < 8; ++w2) v += s_red[w2][kNMax * kNMax + e];
     pi_out[e] += v;
+  }
+}
+
+// Same post-pass for small n (<= 6): lanes run over TIME, each lane keeps all n*n + n accumulators
+// in registers, so a (pair, t) step costs ~10 warp-instructions instead of ~100.
+template <int N>
+__global__ void __launch_bounds__(256) ik_counts_small_kernel(const CountsArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  double aoff[N * N];
+#pragma unroll
+  for (int e = 0; e < N * N; ++e) aoff[e] = (e / N == e % N) ? 0.0 : a.trans[e];
+  double acc_t[N * N], acc_i[N];
+#pragma unroll
+  for (int e = 0; e < N * N; ++e) acc_t[e] = 0.0;
+#pragma unroll
+  for (int e = 0; e < N; ++e) acc_i[e] = 0.0;
+  for (int64_t pair = a.lo + gw; pair < a.hi; pair += a.total_warps) {
+    const int T = a.phone_off[pair + 1] - a.phone_off[pair];
+    const double* st = a.stats + 4 * a.slot_off[pair];
+    for (int t = lane; t < T; t += 32) {
+      const double* row = st + (size_t)t * 4 * N;
+      double f[N], Ft = 0.0;
+#pragma unroll
+      for (int r = 0; r < N; ++r) { f[r] = __ldcg(row + N + r); Ft += f[r]; }
+      const double iF = 1.0 / Ft;
+#pragma unroll
+      for (int r = 0; r < N; ++r) acc_i[r] = fma(f[r], iF, acc_i[r]);                 // :355
+      if (t < T - 1) {
+        double sv[N], dgv[N], rn[N], xv[N * N], z = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+          sv[r] = __ldcg(row + r);
+          dgv[r] = __ldcg(row + 2 * N + r);
+          rn[r] = __ldcg(row + 4 * N + 3 * N + r);
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+          for (int c = 0; c < N; ++c) {
+            const double xi = (r == c) ? dgv[r] : (sv[r] * aoff[r * N + c]) * rn[c];    // :388-389
+            xv[r * N + c] = floor_eps(xi);                                             // :396
+            z += xv[r * N + c];
+          }
+        const double iz = 1.0 / z;
+#pragma unroll
+        for (int e = 0; e < N * N; ++e) acc_t[e] = fma(xv[e], iz, acc_t[e]);
+      }
+    }
+  }
+  // lanes -> warp totals (fixed butterfly order), then the CTA's 8 warps in fixed order
+  __shared__ double s_red[8][N * N + N];
+  const int wic = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < N * N; ++e) {
+    double v = warp_sum_all(acc_t[e]);
+    if (lane == 0) s_red[wic][e] = v;
+  }
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+    double v = warp_sum_all(acc_i[e]);
+    if (lane == 0) s_red[wic][N * N + e] = v;
+  }
+  __syncthreads();
+  double* pt = a.part_trans + ((size_t)blockIdx.x * (kNMax + 1) + N) * (kNMax * kNMax);
+  double* pi_out = a.part_init + ((size_t)blockIdx.x * (kNMax + 1) + N) * kNMax;
+  for (int e = threadIdx.x; e < N * N + N; e += blockDim.x) {
+    double v = 0.0;
+    for (int w2 = 0; w2 < 8; ++w2) v += s_red[w2][e];
+    if (e < N * N) pt[e] += v;
+    else pi_out[e - N * N] += v;
   }
 }
 
@@ -418,6 +540,10 @@ ik_estep_kernel(const EstepArgs a) {
 // ------------------------------------------------------------------------------------------
 static int kg_for(int K) { return (K + kLanesPerRow - 1) / kLanesPerRow; }
 
+// (KG, n) combinations compiled with a static n: the MSCOCO (K=65..72) and Flickr (K=97..104)
+// concept counts for every n <= 10; everything else runs the generic kernel.
+static bool estep_static_n(int n, int KG) { return (KG == 9 || KG == 13) && n >= 1 && n <= 10; }
+
 struct EstepPlan {
   int KG, KS, PP, B, NC, threads, grid, tab;
   size_t smem;
@@ -425,7 +551,7 @@ struct EstepPlan {
 };
 
 static size_t estep_fixed_smem(int PP, int K, int P, int Tmax, int tab) {
-  return ((size_t)2 * PP * NQ * kNMax + kNMax * kNMax + 2 * kNMax + (size_t)2 * PP * K +
+  return ((size_t)2 * PP * kNMax + kNMax * kNMax + 2 * kNMax + PP + (size_t)2 * PP * K +
           (tab ? (size_t)P * K : 0)) * sizeof(double) + (size_t)PP * Tmax * sizeof(int) + 64;
 }
 
@@ -458,7 +584,7 @@ static EstepPlan plan_bucket(int n, int K, int P, int Tmax, int64_t npairs) {
   int64_t nquads = (npairs + pl.PP - 1) / pl.PP;
   int per_sm = (int)(smem_sm / (pl.smem + 1024));
   int by_threads = 2048 / pl.threads;
-  int by_regs = 65536 / ((n <= 8 ? 128 : 64) * pl.threads);
+  int by_regs = estep_static_n(n, pl.KG) ? estep_min_blocks(n) : 1;
   if (per_sm > by_threads) per_sm = by_threads;
   if (per_sm > by_regs) per_sm = by_regs;
   if (per_sm > kEstepCtasPerSm) per_sm = kEstepCtasPerSm;
@@ -467,13 +593,13 @@ static EstepPlan plan_bucket(int n, int K, int P, int Tmax, int64_t npairs) {
   if (grid > nquads) grid = nquads;
   if (grid < 1) grid = 1;
   pl.grid = (int)grid;
-  pl.cta_scratch = (int64_t)pl.PP * ((int64_t)pl.NC * n * pl.KS + (int64_t)Tmax * 2 * n);
+  pl.cta_scratch = (int64_t)pl.PP * ((int64_t)pl.NC * n * pl.KS + (int64_t)Tmax * n);
   return pl;
 }
 
-template <int KG, int NJ, int PP, bool TAB>
+template <int KG, int NN, bool TAB>
 static int launch_estep(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
-  auto kern = ik_estep_kernel<KG, NJ, PP, TAB>;
+  auto kern = ik_estep_kernel<KG, NN, TAB>;
   MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)pl.smem));
   kern<<<pl.grid, pl.threads, pl.smem, st>>>(args);
@@ -481,14 +607,33 @@ static int launch_estep(const EstepArgs& args, const EstepPlan& pl, cudaStream_t
   return 0;
 }
 
+template <int KG, int NN>
+static int launch_estep_tab(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
+  if (pl.tab) return launch_estep<KG, NN, true>(args, pl, st);
+  return launch_estep<KG, NN, false>(args, pl, st);
+}
+
+template <int KG>
+static int launch_estep_static(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
+  switch (args.n) {
+#define MWD_N(V) case V: return launch_estep_tab<KG, V>(args, pl, st);
+    MWD_N(1) MWD_N(2) MWD_N(3) MWD_N(4) MWD_N(5) MWD_N(6) MWD_N(7) MWD_N(8) MWD_N(9) MWD_N(10)
+#undef MWD_N
+  }
+  return launch_estep_tab<KG, 0>(args, pl, st);
+}
+
 template <int KG>
 static int launch_estep_kg(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
-  if (args.n <= 8) {
-    if (pl.tab) return launch_estep<KG, 1, kPairsPerCta, true>(args, pl, st);
-    return launch_estep<KG, 1, kPairsPerCta, false>(args, pl, st);
-  }
-  if (pl.tab) return launch_estep<KG, 2, kPairsPerCta, true>(args, pl, st);
-  return launch_estep<KG, 2, kPairsPerCta, false>(args, pl, st);
+  return launch_estep_tab<KG, 0>(args, pl, st);
+}
+template <>
+int launch_estep_kg<9>(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
+  return launch_estep_static<9>(args, pl, st);
+}
+template <>
+int launch_estep_kg<13>(const EstepArgs& args, const EstepPlan& pl, cudaStream_t st) {
+  return launch_estep_static<13>(args, pl, st);
 }
 
 }  // namespace mwd
@@ -510,6 +655,7 @@ extern "C" int64_t mwd_ik_scratch_bytes(const mwd_ik_problem* p) {
 static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
   MWD_REQUIRE(p->n_concepts >= 1 && p->n_concepts <= MWD_KMAX, "n_concepts %d outside [1,%d]",
               p->n_concepts, MWD_KMAX);
+  MWD_REQUIRE(ll_only || (p->stats != nullptr && p->slot_off != nullptr), "mwd_ik_estep needs stats and slot_off");
   cudaStream_t st = as_stream(stream);
   for (int b = 0; b < p->n_buckets; ++b) {
     const int n = p->bucket_n[b];
@@ -539,6 +685,8 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     a.part_init = p->part_init;
     a.part_trans = p->part_trans;
     a.scratch = p->scratch;
+    a.stats = p->stats;
+    a.slot_off = p->slot_off;
     a.lo = lo;
     a.hi = hi;
     a.cta_scratch = pl.cta_scratch;
@@ -560,6 +708,29 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
         return 2;
     }
     if (rc) return rc;
+    if (!ll_only) {
+      CountsArgs c;
+      c.phone_off = p->phone_off;
+      c.trans = a.trans;
+      c.stats = p->stats;
+      c.slot_off = p->slot_off;
+      c.part_init = p->part_init;
+      c.part_trans = p->part_trans;
+      c.lo = lo;
+      c.hi = hi;
+      c.n = n;
+      c.total_warps = estep_grid_rows() * 8;     // one partial row per CTA, 8 warps per CTA
+      switch (n) {
+        case 1: ik_counts_small_kernel<1><<<estep_grid_rows(), 256, 0, st>>>(c); break;
+        case 2: ik_counts_small_kernel<2><<<estep_grid_rows(), 256, 0, st>>>(c); break;
+        case 3: ik_counts_small_kernel<3><<<estep_grid_rows(), 256, 0, st>>>(c); break;
+        case 4: ik_counts_small_kernel<4><<<estep_grid_rows(), 256, 0, st>>>(c); break;
+        case 5: ik_counts_small_kernel<5><<<estep_grid_rows(), 256, 0, st>>>(c); break;
+        case 6: ik_counts_small_kernel<6><<<estep_grid_rows(), 256, 0, st>>>(c); break;
+        default: ik_counts_kernel<<<estep_grid_rows(), 256, 0, st>>>(c); break;
+      }
+      MWD_CHECK_LAUNCH();
+    }
   }
   return 0;
 }

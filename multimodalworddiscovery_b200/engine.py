@@ -89,6 +89,10 @@ class IKEngine(object):
         self._lens = np.ascontiguousarray(np.array(packed.lens, dtype=np.int32))
         self.toeplitz = 1 if len(packed.lens) >= 6 else 0     # :399
         self.n_pairs_global = int(packed.n_pairs_global)
+        # per-step row statistics handed from the recursion kernel to the count post-pass
+        slot = packed.ap_offsets()
+        self.slot_off = torch.from_numpy(slot).to(dev)
+        self.stats = torch.empty((max(4 * int(slot[-1]), 1),), dtype=f64, device=dev)
         # checkpoint scratch
         self.scratch = None
         prob = self._problem()
@@ -120,6 +124,7 @@ class IKEngine(object):
         p.part_trans = _ptr(self._part_trans)
         p.scratch = _ptr(self.scratch)
         p.scratch_bytes = self.scratch.numel() * 8 if self.scratch is not None else 0
+        p.stats, p.slot_off = _ptr(self.stats), _ptr(self.slot_off)
         return p
 
     # ------------------------------------------------------------------ parameters
@@ -263,6 +268,7 @@ class IKEngine(object):
         p.region_off = _ptr(self.region_off[lo:])
         p.phone_off = _ptr(self.phone_off[lo:])
         p.pair_ll = _ptr(self.pair_ll[lo:])
+        p.slot_off = _ptr(self.slot_off[lo:])
         if for_grad:   # the gradient GEMM walks rows [0, n_regions) of the arrays it is given
             p.n_regions = r_hi - r_lo
             p.feats = _ptr(self.feats[r_lo:r_hi])
