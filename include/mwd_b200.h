@@ -242,6 +242,11 @@ typedef struct {
   double* part_trans;         /* [dev] hmm_warps x (NMAX+1) x NMAX*NMAX                      */
   double* alpha_out;          /* [dev] n_slots or NULL: forward()  values                    */
   double* beta_out;           /* [dev] n_slots or NULL: backward() values                    */
+  const double* emis;         /* [dev] n_slots or NULL: dense log emissions lb[t][j] (segment-
+                                 embedding model); when set, `obs` is not read                */
+  int64_t n_src_rows;         /* src_off[N] (segment model: rows of the embedding matrix)     */
+  const int32_t* row_pair;    /* [dev] n_src_rows: pair of each source row (segment model)    */
+  const int32_t* slot_row;    /* [dev] n_slots: source row of each slot       (segment model) */
 } mwd_hmm_problem;
 
 /* number of persistent warps (= rows of part_init / part_trans)                              */
@@ -265,7 +270,7 @@ int mwd_hmm_reduce(const mwd_hmm_problem* p, const int64_t* post_idx, const int6
  * audio_hmm_word_discoverer.py:354-389 (counts first merged into the running log accumulators
  * `acc`, which persist over epochs like the reference's count lists).                        */
 typedef struct {
-  int32_t log_domain, n_tgt_types, n_src_types, n_lens;
+  int32_t log_domain, n_tgt_types, n_src_types, n_lens;   /* n_src_types == 0: skip the obs table */
   const int32_t* lens;        /* [host]                                                      */
   const double* counts;       /* [dev]                                                       */
   double* acc;                /* [dev] running log accumulators (log domain only), same layout*/
@@ -280,6 +285,26 @@ int mwd_hmm_mstep(const mwd_hmm_mstep_args* a, void* stream);
  *   align_probs [dev] sum_p (T_p - 1) * n_p doubles or NULL, pair p at ap_off[p]             */
 int mwd_hmm_align(const mwd_hmm_problem* p, double unk_prob, int32_t* alignment, double* align_probs,
                   const int64_t* ap_off, void* stream);
+
+/* ---- segment-embedding HMM (hmm/audio_segembed_hmm_word_discoverer.py + the emission model it
+ * was written against, smt/audio_gmm_word_discoverer.py:53-61,395-401): source "tokens" are
+ * rows of emb[S][D]; state j of pair p emits x_t with
+ *     lb[t][j] = LSE_m( lprior[w][m] + log N(x_t; means[w][m], diag var[w][m]) ),  w = tgt[j].
+ * mwd_hmm_gauss_emission fills emis (n_slots) and the log mixture responsibilities resp
+ * (n_slots x M); lnorm [dev] Vt x M is scratch.                                              */
+int mwd_hmm_gauss_emission(const mwd_hmm_problem* p, const void* emb, int emb_is_f64, int emb_dim,
+                           int n_mix, const double* lprior, const double* means, const double* var,
+                           double* lnorm, double* emis, double* resp, void* stream);
+/* Posterior-weighted sufficient statistics per (word, mixture): stats[w][m] = [sum wgt,
+ * sum wgt*x (D), sum wgt*x^2 (D)], wgt = exp(post + resp); slots are visited through a postings
+ * index sorted by word (word_idx, word_off[Vt+1]) in fixed order (smt/...:339-375).          */
+int mwd_hmm_gauss_stats(const mwd_hmm_problem* p, const void* emb, int emb_is_f64, int emb_dim,
+                        int n_mix, const double* resp, const int64_t* word_idx, const int64_t* word_off,
+                        double* stats, void* stream);
+/* means = sum wgt*x / sum wgt; mixture priors renormalised when n_mix > 1; variances only when
+ * update_var != 0 (the reference's fixedVariance > 0 keeps them).                            */
+int mwd_hmm_gauss_update(int n_tgt_types, int n_mix, int emb_dim, const double* stats, int update_var,
+                         double* lprior, double* means, double* var, void* stream);
 
 #ifdef __cplusplus
 }

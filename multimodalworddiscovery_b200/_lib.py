@@ -67,7 +67,8 @@ class HmmProblem(C.Structure):
         ('init', C.c_void_p), ('trans', C.c_void_p), ('obs', C.c_void_p),
         ('pair_ll', C.c_void_p), ('post', C.c_void_p),
         ('part_init', C.c_void_p), ('part_trans', C.c_void_p),
-        ('alpha_out', C.c_void_p), ('beta_out', C.c_void_p),
+        ('alpha_out', C.c_void_p), ('beta_out', C.c_void_p), ('emis', C.c_void_p),
+        ('n_src_rows', C.c_int64), ('row_pair', C.c_void_p), ('slot_row', C.c_void_p),
     ]
 
 
@@ -109,6 +110,9 @@ SYMBOLS = {
     'mwd_hmm_reduce': (_i, [C.POINTER(HmmProblem), _vp, _vp, _vp, _vp]),
     'mwd_hmm_mstep': (_i, [C.POINTER(HmmMstepArgs), _vp]),
     'mwd_hmm_align': (_i, [C.POINTER(HmmProblem), _d, _vp, _vp, _vp, _vp]),
+    'mwd_hmm_gauss_emission': (_i, [C.POINTER(HmmProblem), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'mwd_hmm_gauss_stats': (_i, [C.POINTER(HmmProblem), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'mwd_hmm_gauss_update': (_i, [_i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -35,6 +35,7 @@ struct HmmArgs {
   double* part_trans;
   double* alpha_out;
   double* beta_out;
+  const double* emis;    // dense log emissions (n_slots) or null
   int64_t lo, hi;
   int n, Vf, Tmax, warps_per_cta, total_warps;
 };
@@ -96,13 +97,14 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
       const double* orow = a.obs + (size_t)ej * Vf;
       const int64_t slot0 = a.slot_off[pair];
       auto emis = [&](int t) -> double {
+        if (LOG && a.emis) return on ? a.emis[slot0 + (int64_t)t * n + j] : 0.0;   // continuous model
         double b = on ? orow[f[t]] : 0.0;
         return (b != b) ? 0.0 : b;           // absent pair: 0 in both classes (:122 / :161)
       };
       // ------------------------------------------------------------ forward
       double al;
       {
-        double b0 = on ? orow[f[0]] : 0.0;
+        double b0 = on ? ((LOG && a.emis) ? a.emis[slot0 + j] : orow[f[0]]) : 0.0;
         if (LOG) al = on ? s_pi[j] + b0 : -INFINITY;          // :158 (absent -> KeyError upstream)
         else al = on ? s_pi[j] * ((b0 != b0) ? 0.0 : b0) : 0.0;   // :114-118
       }
@@ -394,6 +396,8 @@ struct HmmAlignArgs {
   int32_t* alignment;
   double* align_probs;
   const int64_t* ap_off;
+  const double* emis;
+  const int64_t* slot_off;
   int64_t n_pairs;
   int Vf, Tmax, warps_per_cta;
   double unk;
@@ -424,9 +428,10 @@ __global__ void __launch_bounds__(256) hmm_align_kernel(const HmmAlignArgs a) {
   const double* pi = a.init + (size_t)n * MWD_INIT_STRIDE;
   const double* orow = a.obs + (size_t)(on ? a.tgt[e0 + j] : 0) * a.Vf;
   double* ap = a.align_probs ? a.align_probs + a.ap_off[pair] : nullptr;
+  const int64_t slot0 = a.emis ? a.slot_off[pair] : 0;
   double sc = 0.0;
   if (on) {
-    double b0 = orow[f[0]];
+    double b0 = a.emis ? a.emis[slot0 + j] : orow[f[0]];
     sc = LOG ? pi[j] + b0 : pi[j] * b0;                       // :307 / :402
     s_sc[j] = sc;
   }
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(256) hmm_align_kernel(const HmmAlignArgs a) {
     const double* prev = s_sc + ((t - 1) & 1) * kNMax;
     double* next = s_sc + (t & 1) * kNMax;
     if (on) {
-      double b = orow[f[t]];
+      double b = a.emis ? a.emis[slot0 + (int64_t)t * n + j] : orow[f[t]];
       if (b != b) b = a.unk;                                  // :311 / :407
       double best = LOG ? __dadd_rn(__dadd_rn(prev[0], A[j]), b) : __dmul_rn(__dmul_rn(prev[0], A[j]), b);
       int arg = 0;
@@ -470,6 +475,112 @@ __global__ void __launch_bounds__(256) hmm_align_kernel(const HmmAlignArgs a) {
       cur = s_bp[t * kNMax + cur];
       a.alignment[f0 + t - 1] = cur;
     }
+  }
+}
+
+// ---------------------------------------------------------------- Gaussian segment emissions
+// lnorm[w][m] = -(D/2 log 2pi + 1/2 sum_d log var)   (smt/audio_gmm_word_discoverer.py:58)
+__global__ void gauss_lnorm_kernel(const double* __restrict__ var, int D, double* __restrict__ lnorm) {
+  const int wm = blockIdx.x;
+  double s = 0.0;
+  for (int d = threadIdx.x; d < D; d += 32) s += log(var[(size_t)wm * D + d]);
+  s = warp_sum(s);
+  if (threadIdx.x == 0) lnorm[wm] = -(0.5 * D * log(2.0 * 3.14159265358979323846) + 0.5 * s);
+}
+
+// one warp per (pair, t): lanes over the embedding dimensions
+template <typename FT>
+__global__ void __launch_bounds__(256) gauss_emission_kernel(
+    const int32_t* __restrict__ tgt_off, const int32_t* __restrict__ tgt, const int32_t* __restrict__ src_off,
+    const int64_t* __restrict__ slot_off, int64_t n_pairs, const FT* __restrict__ emb, int D, int M,
+    const double* __restrict__ lprior, const double* __restrict__ means, const double* __restrict__ var,
+    const double* __restrict__ lnorm, double* __restrict__ emis, double* __restrict__ resp, int64_t n_rows,
+    const int32_t* __restrict__ row_pair) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // embedding row
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const int pair = row_pair[row];
+  const int t = (int)(row - src_off[pair]);
+  const int e0 = tgt_off[pair];
+  const int n = tgt_off[pair + 1] - e0;
+  const FT* x = emb + row * D;
+  const int64_t slot = slot_off[pair] + (int64_t)t * n;
+  for (int j = 0; j < n; ++j) {
+    const int w = tgt[e0 + j];
+    double comp[8];
+    double mx = -INFINITY;
+    for (int m = 0; m < M; ++m) {
+      const double* mu = means + ((size_t)w * M + m) * D;
+      const double* vr = var + ((size_t)w * M + m) * D;
+      double q = 0.0;
+      for (int d = lane; d < D; d += 32) {
+        const double z = (double)x[d] - mu[d];
+        q += z * z / (2.0 * vr[d]);
+      }
+      q = warp_sum(q);
+      comp[m] = lprior[w * M + m] + lnorm[w * M + m] - q;                 // :59, :395-401
+      mx = fmax(mx, comp[m]);
+    }
+    if (!(fabs(mx) < INFINITY)) mx = 0.0;
+    double s = 0.0;
+    for (int m = 0; m < M; ++m) s += exp(comp[m] - mx);
+    const double lb = log(s) + mx;
+    if (lane == 0) {
+      emis[slot + j] = lb;
+      for (int m = 0; m < M; ++m) resp[(slot + j) * M + m] = comp[m] - lb;
+    }
+  }
+}
+
+// one CTA per word; thread d owns dimension d; slots of the word in postings order
+template <typename FT>
+__global__ void __launch_bounds__(128) gauss_stats_kernel(
+    const int64_t* __restrict__ word_idx, const int64_t* __restrict__ word_off,
+    const int32_t* __restrict__ slot_row, const FT* __restrict__ emb, int D, int M,
+    const double* __restrict__ post, const double* __restrict__ resp, double* __restrict__ stats) {
+  const int w = blockIdx.x;
+  const int64_t lo = word_off[w], hi = word_off[w + 1];
+  const int SW = 1 + 2 * D;
+  for (int m = 0; m < M; ++m) {
+    double* out = stats + ((size_t)w * M + m) * SW;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      double sx = 0.0, sxx = 0.0, sw = 0.0;
+      for (int64_t q = lo; q < hi; ++q) {
+        const int64_t slot = word_idx[q];
+        const double wg = exp(post[slot] + resp[slot * M + m]);
+        const double xv = (double)emb[(size_t)slot_row[slot] * D + d];
+        sw += wg;
+        sx = fma(wg, xv, sx);
+        sxx = fma(wg, xv * xv, sxx);
+      }
+      out[1 + d] = sx;
+      out[1 + D + d] = sxx;
+      if (d == 0) out[0] = sw;
+    }
+  }
+}
+
+__global__ void gauss_update_kernel(int M, int D, const double* __restrict__ stats, int update_var,
+                                    double* __restrict__ lprior, double* __restrict__ means,
+                                    double* __restrict__ var) {
+  const int w = blockIdx.x;
+  const int SW = 1 + 2 * D;
+  double tot = 0.0;
+  for (int m = 0; m < M; ++m) tot += stats[((size_t)w * M + m) * SW];
+  for (int m = 0; m < M; ++m) {
+    const double* st = stats + ((size_t)w * M + m) * SW;
+    const double sw = st[0];
+    if (sw > 0.0) {
+      for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const double mu = st[1 + d] / sw;
+        means[((size_t)w * M + m) * D + d] = mu;
+        if (update_var) {
+          double v = st[1 + D + d] / sw - mu * mu;
+          var[((size_t)w * M + m) * D + d] = v < 1e-6 ? 1e-6 : v;
+        }
+      }
+    }
+    if (M > 1 && tot > 0.0 && threadIdx.x == 0) lprior[w * M + m] = log(sw / tot);
   }
 }
 
@@ -511,6 +622,7 @@ extern "C" int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream) {
     a.pair_ll = p->pair_ll; a.post = p->post;
     a.part_init = p->part_init; a.part_trans = p->part_trans;
     a.alpha_out = p->alpha_out; a.beta_out = p->beta_out;
+    a.emis = p->emis;
     a.lo = lo; a.hi = hi; a.n = n; a.Vf = p->n_src_types; a.Tmax = Tmax;
     a.warps_per_cta = wpc; a.total_warps = total;
     const size_t smem = fixed + (size_t)wpc * per_warp;
@@ -535,7 +647,7 @@ extern "C" int mwd_hmm_reduce(const mwd_hmm_problem* p, const int64_t* post_idx,
   const int64_t te = (int64_t)(kNMax + 1) * kNMax * kNMax;
   const unsigned og = (unsigned)((oe + 7) / 8);
   if (p->log_domain) {
-    hmm_postings_kernel<true><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
+    if (!p->emis) hmm_postings_kernel<true><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
     hmm_reduce_rows_kernel<true><<<(unsigned)((ie + 255) / 256), 256, 0, st>>>(p->part_init, rows, ie, counts + oe);
     hmm_reduce_rows_kernel<true><<<(unsigned)((te + 255) / 256), 256, 0, st>>>(p->part_trans, rows, te, counts + oe + ie);
   } else {
@@ -567,7 +679,7 @@ extern "C" int mwd_hmm_mstep(const mwd_hmm_mstep_args* a, void* stream) {
     MWD_REQUIRE(a->acc != nullptr, "log-domain M-step needs the running accumulators");
     hmm_mstep_init_trans_kernel<true><<<a->n_lens, 64, 0, st>>>(la, initC, transC, a->acc + oe, a->acc + oe + ie,
                                                              a->init, a->trans);
-    hmm_mstep_obs_kernel<true><<<(Vt + 7) / 8, 256, 0, st>>>(obsC, a->acc, Vt, Vf, a->obs);
+    if (Vf > 0) hmm_mstep_obs_kernel<true><<<(Vt + 7) / 8, 256, 0, st>>>(obsC, a->acc, Vt, Vf, a->obs);
   } else {
     hmm_mstep_init_trans_kernel<false><<<a->n_lens, 64, 0, st>>>(la, initC, transC, nullptr, nullptr, a->init,
                                                               a->trans);
@@ -586,6 +698,7 @@ extern "C" int mwd_hmm_align(const mwd_hmm_problem* p, double unk_prob, int32_t*
   a.tgt_off = p->tgt_off; a.tgt = p->tgt; a.src_off = p->src_off; a.src = p->src;
   a.init = p->init; a.trans = p->trans; a.obs = p->obs;
   a.alignment = alignment; a.align_probs = align_probs; a.ap_off = ap_off;
+  a.emis = p->emis; a.slot_off = p->slot_off;
   a.n_pairs = p->n_pairs; a.Vf = p->n_src_types; a.Tmax = p->t_max; a.unk = unk_prob;
   size_t per_warp = 2 * kNMax * sizeof(double) + (size_t)a.Tmax * kNMax;
   per_warp = (per_warp + 7) / 8 * 8;
@@ -603,6 +716,49 @@ extern "C" int mwd_hmm_align(const mwd_hmm_problem* p, double unk_prob, int32_t*
     MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hmm_align_kernel<false><<<(unsigned)grid, wpc * 32, smem, st>>>(a);
   }
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mwd_hmm_gauss_emission(const mwd_hmm_problem* p, const void* emb, int emb_is_f64, int D,
+                                      int M, const double* lprior, const double* means, const double* var,
+                                      double* lnorm, double* emis, double* resp, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  MWD_REQUIRE(M >= 1 && M <= 8, "n_mix %d outside [1,8]", M);
+  MWD_REQUIRE(p->row_pair != nullptr, "segment model needs row_pair");
+  const int64_t rows = p->n_src_rows;
+  gauss_lnorm_kernel<<<p->n_tgt_types * M, 32, 0, st>>>(var, D, lnorm);
+  if (rows > 0) {
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (emb_is_f64)
+      gauss_emission_kernel<double><<<grid, 256, 0, st>>>(p->tgt_off, p->tgt, p->src_off, p->slot_off, p->n_pairs,
+          (const double*)emb, D, M, lprior, means, var, lnorm, emis, resp, rows, p->row_pair);
+    else
+      gauss_emission_kernel<float><<<grid, 256, 0, st>>>(p->tgt_off, p->tgt, p->src_off, p->slot_off, p->n_pairs,
+          (const float*)emb, D, M, lprior, means, var, lnorm, emis, resp, rows, p->row_pair);
+  }
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mwd_hmm_gauss_stats(const mwd_hmm_problem* p, const void* emb, int emb_is_f64, int D, int M,
+                                   const double* resp, const int64_t* word_idx, const int64_t* word_off,
+                                   double* stats, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  MWD_REQUIRE(p->slot_row != nullptr, "segment model needs slot_row");
+  if (emb_is_f64)
+    gauss_stats_kernel<double><<<p->n_tgt_types, 128, 0, st>>>(word_idx, word_off, p->slot_row, (const double*)emb,
+                                                              D, M, p->post, resp, stats);
+  else
+    gauss_stats_kernel<float><<<p->n_tgt_types, 128, 0, st>>>(word_idx, word_off, p->slot_row, (const float*)emb,
+                                                             D, M, p->post, resp, stats);
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mwd_hmm_gauss_update(int Vt, int M, int D, const double* stats, int update_var,
+                                    double* lprior, double* means, double* var, void* stream) {
+  gauss_update_kernel<<<Vt, 128, 0, as_stream(stream)>>>(M, D, stats, update_var, lprior, means, var);
   MWD_CHECK_LAUNCH();
   return 0;
 }

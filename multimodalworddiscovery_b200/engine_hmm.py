@@ -81,6 +81,8 @@ class PackedSentences(object):
         i_of_slot = np.arange(self.n_slots) - np.repeat(first_slot, rep)
         tgt_idx = self.tgt_off[pair_of_pos[pos_of_slot]].astype(np.int64) + i_of_slot
         keys = self.tgt[tgt_idx].astype(np.int64) * self.Vf + self.src[pos_of_slot].astype(np.int64)
+        self.slot_row = pos_of_slot.astype(np.int32)      # source row (phone position / segment) of each slot
+        self.row_pair = pair_of_pos.astype(np.int32)      # pair of each source row
         idx = np.argsort(keys, kind='stable').astype(np.int64)
         off = np.searchsorted(keys[idx], np.arange(n_tgt_types * self.Vf + 1)).astype(np.int64)
         return idx, off
@@ -152,6 +154,9 @@ class PlainHMMEngine(object):
         p.pair_ll, p.post = _ptr(self.pair_ll), _ptr(self.post)
         p.part_init, p.part_trans = _ptr(self.part_init), _ptr(self.part_trans)
         p.alpha_out, p.beta_out = _ptr(alpha), _ptr(beta)
+        p.emis = _ptr(getattr(self, 'emis', None))
+        p.n_src_rows = len(pk.src)
+        p.row_pair, p.slot_row = _ptr(getattr(self, 'row_pair', None)), _ptr(getattr(self, 'slot_row', None))
         return p
 
     # ------------------------------------------------------------------ parameters
@@ -220,3 +225,80 @@ class PlainHMMEngine(object):
         be = torch.zeros_like(al)
         self.estep(al, be)
         return al, be
+
+
+class SegmentHMMEngine(PlainHMMEngine):
+    """Log-domain HMM over [NULL]+concepts with diagonal-Gaussian(-mixture) emissions on segment
+    embeddings (the acoustic model hmm/audio_segembed_hmm_word_discoverer.py was written against).
+    Source "tokens" are rows of the embedding matrix; everything else reuses the plain-state kernels
+    with dense emissions."""
+
+    def __init__(self, tgt_ids, embeddings, n_tgt_types, n_mix, device=None, rank=0, world=1,
+                 emb_dtype=np.float32):
+        seg_ids = [np.zeros(len(x), dtype=np.int32) for x in embeddings]
+        pk = PackedSentences(tgt_ids, seg_ids, 1, rank=rank, world=world)
+        PlainHMMEngine.__init__(self, pk, n_tgt_types, 1, True, device=device)
+        torch = self.torch
+        dev, f64 = self.device, torch.float64
+        self.Vf = 0                                   # no discrete observation table on the device path
+        self.counts_len = int(self.lib.mwd_hmm_counts_len(self.Vt, 0))
+        self.counts = torch.zeros((self.counts_len,), dtype=f64, device=dev)
+        self.reset_accumulators()
+        self.M = int(n_mix)
+        self.D = int(embeddings[0].shape[1])
+        rows = np.concatenate([np.asarray(embeddings[i]).reshape(-1, self.D) for i in pk.order], axis=0)
+        self.emb = torch.from_numpy(np.ascontiguousarray(rows, dtype=emb_dtype)).to(dev)
+        self.emb_is_f64 = 1 if emb_dtype == np.float64 else 0
+        self.row_pair = torch.from_numpy(pk.row_pair).to(dev)
+        self.slot_row = torch.from_numpy(pk.slot_row).to(dev)
+        self.emis = torch.zeros((max(pk.n_slots, 1),), dtype=f64, device=dev)
+        self.resp = torch.zeros((max(pk.n_slots, 1), self.M), dtype=f64, device=dev)
+        self.lprior = torch.zeros((self.Vt, self.M), dtype=f64, device=dev)
+        self.means = torch.zeros((self.Vt, self.M, self.D), dtype=f64, device=dev)
+        self.var = torch.ones((self.Vt, self.M, self.D), dtype=f64, device=dev)
+        self.lnorm = torch.zeros((self.Vt, self.M), dtype=f64, device=dev)
+        self.stats = torch.zeros((self.Vt, self.M, 1 + 2 * self.D), dtype=f64, device=dev)
+
+    def set_emission_params(self, lprior, means, var):
+        torch = self.torch
+        self.lprior.copy_(torch.from_numpy(np.ascontiguousarray(lprior, dtype=np.float64)))
+        self.means.copy_(torch.from_numpy(np.ascontiguousarray(means, dtype=np.float64)))
+        self.var.copy_(torch.from_numpy(np.ascontiguousarray(var, dtype=np.float64)))
+
+    def set_chain_params(self, init, trans):
+        it, tt = tables_to_dense(init, trans)
+        self.init_t.copy_(self.torch.from_numpy(it))
+        self.trans_t.copy_(self.torch.from_numpy(tt))
+
+    def get_all_params(self):
+        init, trans = dense_to_tables(self.init_t.cpu().numpy(), self.trans_t.cpu().numpy(), self.pk.lens)
+        return init, trans, self.lprior.cpu().numpy(), self.means.cpu().numpy(), self.var.cpu().numpy()
+
+    def emission(self):
+        prob = self._problem()
+        _lib.check(self.lib.mwd_hmm_gauss_emission(C.byref(prob), _ptr(self.emb), self.emb_is_f64, self.D, self.M,
+                                                   _ptr(self.lprior), _ptr(self.means), _ptr(self.var),
+                                                   _ptr(self.lnorm), _ptr(self.emis), _ptr(self.resp), self._stream()))
+
+    def estep(self, alpha=None, beta=None):
+        self.emission()
+        PlainHMMEngine.estep(self, alpha, beta)
+
+    def em_iteration(self, update_var=False):
+        self.estep()
+        self.allreduce()
+        ll = self.counts[self.counts_len - 1].clone()
+        self.mstep()
+        prob = self._problem()
+        st = self._stream()
+        _lib.check(self.lib.mwd_hmm_gauss_stats(C.byref(prob), _ptr(self.emb), self.emb_is_f64, self.D, self.M,
+                                                _ptr(self.resp), _ptr(self.post_idx), _ptr(self.post_off),
+                                                _ptr(self.stats), st))
+        fixed_order_allreduce(self.stats, self.pg)
+        _lib.check(self.lib.mwd_hmm_gauss_update(self.Vt, self.M, self.D, _ptr(self.stats), 1 if update_var else 0,
+                                                 _ptr(self.lprior), _ptr(self.means), _ptr(self.var), st))
+        return ll
+
+    def align(self, unk_prob=10e-12):
+        self.emission()
+        return PlainHMMEngine.align(self, unk_prob)
