@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(128) ik_decode_kernel(const DecodeArgs a) {
   double* s_p = s_pz + kNMax * K;                   // [Tmax][n]
   double* s_sc = s_p + (size_t)a.Tmax * kNMax;      // [2][NMAX]
   int* s_x = reinterpret_cast<int*>(s_sc + 2 * kNMax);     // [Tmax]
-  unsigned char* s_bp = reinterpret_cast<unsigned char*>(s_x + a.Tmax);  // [Tmax][NMAX]
+  unsigned char* s_bp = reinterpret_cast<unsigned char*>(s_x) + (((size_t)a.Tmax * sizeof(int) + 7) & ~(size_t)7);  // [Tmax][NMAX]
+  // cluster scores [n][K] live in their own region after the back-pointers (8-byte aligned)
+  double* s_cl = reinterpret_cast<double*>(s_bp + (((size_t)a.Tmax * kNMax + 7) & ~(size_t)7));
 
   for (int e = tid; e < n * K; e += blockDim.x) s_pz[e] = a.pz[r0 * K + e];
   for (int t = tid; t < T; t += blockDim.x) s_x[t] = ph[t];
@@ -118,8 +120,6 @@ __global__ void __launch_bounds__(128) ik_decode_kernel(const DecodeArgs a) {
   }
   __syncthreads();
   // cluster (:586-597): scores[i][k] = pz[i][k] * prod_{t: align[t]==i} obs[k][x_t], in t order
-  double* s_cl = s_p;  // reuse: [n][K]
-  __syncthreads();
   for (int e = tid; e < n * K; e += blockDim.x) {
     int i = e / K, k = e - i * K;
     double sc = s_pz[e];
@@ -269,10 +269,10 @@ extern "C" int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int given_
   a.floor_norm = floor_norm;
   a.given_alignment = given_alignment;
   a.cluster_scores = cluster_scores;
+  // s_pz [NMAX][K] | s_p [Tmax][NMAX] | s_sc [2][NMAX] | s_x [Tmax] ints | s_bp [Tmax][NMAX] bytes | s_cl [NMAX][K]
   size_t smem = ((size_t)kNMax * a.K + (size_t)a.Tmax * kNMax + 2 * kNMax) * sizeof(double) +
-                (size_t)a.Tmax * sizeof(int) + (size_t)a.Tmax * kNMax;
-  if ((size_t)kNMax * a.K > (size_t)a.Tmax * kNMax)  // cluster scores reuse the p[t][i] area
-    smem += ((size_t)kNMax * a.K - (size_t)a.Tmax * kNMax) * sizeof(double);
+                (((size_t)a.Tmax * sizeof(int) + 7) & ~(size_t)7) + (((size_t)a.Tmax * kNMax + 7) & ~(size_t)7) +
+                (size_t)kNMax * a.K * sizeof(double);
   MWD_REQUIRE(smem <= 227 * 1024, "decode shared memory %zu exceeds 227 KB (t_max=%d)", smem, a.Tmax);
   if (smem > 48 * 1024)
     MWD_CHECK_CUDA(cudaFuncSetAttribute(ik_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -21,6 +21,8 @@
 //     never sits on the recursion's critical path;
 //   * counts are accumulated without atomics: init/trans in registers of fixed warps, phone
 //     counts by read-modify-write of a per-CTA table that only this CTA touches, in t order.
+#include <stdlib.h>
+
 #include "mwd_common.cuh"
 
 namespace mwd {
@@ -72,7 +74,8 @@ __device__ __forceinline__ void drain_column(double* tab, int K, int k, const in
     if (xs[s] >= 0) tab[xs[s] * K + k] = v[s];
 }
 
-constexpr int estep_min_blocks(int nn) { return nn <= 0 ? 1 : (480 / (32 * nn) < 1 ? 1 : 480 / (32 * nn)); }
+constexpr int kEstepThreadsPerSm = 480;   // register budget: 65536 / 480 = 136 per thread (3 x 160-thread CTAs)
+constexpr int estep_min_blocks(int nn) { return nn <= 0 ? 1 : (kEstepThreadsPerSm / (32 * nn) < 1 ? 1 : kEstepThreadsPerSm / (32 * nn)); }
 
 // KG = ceil(K/8) exactly: only the last of a lane's KG concepts can fall outside [0,K).
 // NN > 0: n is a compile-time constant (index math folds, the n-loops unroll); NN == 0: generic.
@@ -560,19 +563,27 @@ static EstepPlan plan_bucket(int n, int K, int P, int Tmax, int64_t npairs) {
   pl.KG = kg_for(K);
   pl.KS = pl.KG * kLanesPerRow;
   pl.PP = kPairsPerCta;
-  pl.tab = ((size_t)P * K * sizeof(double) <= 64 * 1024) ? 1 : 0;
+  // The per-CTA phone-count table lives in global memory by default (L2-resident, ~25 KB per CTA):
+  // measured equal in speed to a shared-memory copy (profiles/r01_bench_history.md) and it leaves
+  // the shared memory to a longer checkpoint interval B, i.e. less checkpoint traffic.
+  // Tuning knobs (experiments only): MWD_ESTEP_TAB=1 (shared-memory table), MWD_ESTEP_CTAS=<target
+  // CTAs/SM>, MWD_ESTEP_B=<minimum checkpoint interval>.
+  pl.tab = 0;
+  if (const char* e = getenv("MWD_ESTEP_TAB")) pl.tab = (atoi(e) && (size_t)P * K * sizeof(double) <= 64 * 1024) ? 1 : 0;
   const size_t fixed = estep_fixed_smem(pl.PP, K, P, Tmax, pl.tab);
   const size_t slice = (size_t)pl.PP * n * pl.KS * sizeof(double);
   pl.threads = pl.PP * n * kLanesPerRow;
   // aim for 3 co-resident CTAs per SM, at least 2 alpha slices per block, at most BMAX
   const size_t smem_sm = 224 * 1024;
   int target = 3;
+  if (const char* e = getenv("MWD_ESTEP_CTAS")) target = atoi(e) > 0 ? atoi(e) : target;
+  const int min_b = getenv("MWD_ESTEP_B") ? atoi(getenv("MWD_ESTEP_B")) : 2;
   int B = 0;
   for (; target >= 1; --target) {
     size_t budget = smem_sm / target;
     if (budget <= fixed + 1024) continue;
     B = (int)((budget - fixed - 1024) / slice);
-    if (B >= 2 || target == 1) break;
+    if (B >= min_b || target == 1) break;
   }
   if (B < 1) B = 1;
   if (B > BMAX) B = BMAX;

@@ -1,0 +1,121 @@
+"""Edge cases of the (i,k)-state path against the oracle: single-phone captions, single-region
+images, the maximum n (16) and K (128), a phone inventory too large for the shared-memory table,
+odd n with the generic (runtime-n) kernel, identical pairs, fp32 vs fp64 feature storage."""
+import numpy as np
+import pytest
+
+from helpers import flatten_tables
+from oracle import image_phone_hmm as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _run(feats, phones, K, P, kind='linear', iters=2, feat_dtype=np.float64, seed=0, width=2.0):
+    from multimodalworddiscovery_b200.corpus import pack_pairs
+    from multimodalworddiscovery_b200.engine import IKEngine
+    rng = np.random.default_rng(seed)
+    D = feats[0].shape[1]
+    obs0 = rng.random((K, P)) + 0.02
+    obs0 /= obs0.sum(1, keepdims=True)
+    if kind == 'linear':
+        p = orc.initial_params(feats, K, P, 'linear', W=0.4 * rng.standard_normal((K, D + 1)), lr=0.05, obs=obs0)
+        post0 = p['W']
+    else:
+        p = orc.initial_params(feats, K, P, 'gaussian', mus=rng.standard_normal((K, D)), width=width, lr=0.05, obs=obs0)
+        post0 = p['mus']
+    pk = pack_pairs(feats, phones, feat_dtype=feat_dtype)
+    eng = IKEngine(pk, K, P, gaussian=(kind == 'gaussian'))
+    eng.set_params(p['init'], p['trans'], p['obs'], post0)
+    lens = sorted(p['init'])
+    for _ in range(iters):
+        p, info = orc.em_iteration(feats, phones, p, kind)
+        ll = float(eng.em_iteration(0.05, 0.0, width)) / len(feats)
+        np.testing.assert_allclose(ll, info['avg_ll'], rtol=RTOL)
+        init, trans, obs, post = eng.get_params()
+        np.testing.assert_allclose(flatten_tables(lens, init), flatten_tables(lens, p['init']), rtol=RTOL)
+        np.testing.assert_allclose(flatten_tables(lens, trans), flatten_tables(lens, p['trans']), rtol=RTOL)
+        np.testing.assert_allclose(obs, p['obs'], rtol=RTOL)
+        np.testing.assert_allclose(post, p['W' if kind == 'linear' else 'mus'], rtol=1e-8, atol=1e-12)
+    # decode parity (bit-exact integers)
+    ali, ic, _ = eng.decode(floor_norm=(kind == 'gaussian'), want_probs=False, width=width)
+    ali, ic = ali.cpu().numpy(), ic.cpu().numpy()
+    for s, ex in enumerate(pk.order):
+        v, x = feats[ex], phones[ex]
+        n = v.shape[0]
+        pz = orc.posterior(v, p, kind)
+        path, _ = orc.align(pz, x, p['obs'], p['init'][n], p['trans'][n], floor_norm=(kind == 'gaussian'))
+        cl, _ = orc.cluster(pz, x, p['obs'], path)
+        assert ali[pk.phone_off[s]:pk.phone_off[s + 1]].tolist() == path
+        assert ic[pk.region_off[s]:pk.region_off[s + 1]].tolist() == cl
+
+
+def _corpus(rng, N, n_choices, T_lo, T_hi, K, P, D):
+    cents = rng.standard_normal((K, D))
+    feats, phones = [], []
+    for _ in range(N):
+        n = int(rng.choice(n_choices))
+        T = int(rng.integers(T_lo, T_hi + 1))
+        feats.append((cents[rng.integers(0, K, n)] + 0.5 * rng.standard_normal((n, D))).astype(np.float32).astype(np.float64))
+        phones.append(rng.integers(0, P, T))
+    return feats, phones
+
+
+def test_single_phone_and_single_region():
+    rng = np.random.default_rng(1)
+    f, x = _corpus(rng, 17, [1, 2, 5], 1, 3, K=6, P=5, D=4)      # T == 1 pairs, n == 1 pairs, ragged quads
+    _run(f, x, 6, 5)
+
+
+def test_max_states_and_concepts():
+    rng = np.random.default_rng(2)
+    f, x = _corpus(rng, 9, [16, 15, 9], 2, 12, K=128, P=7, D=5)   # n = 16, K = 128 (KG = 16), generic kernel
+    _run(f, x, 128, 7, iters=1)
+
+
+def test_static_n_kernels_all_lengths():
+    rng = np.random.default_rng(3)
+    f, x = _corpus(rng, 44, list(range(1, 11)), 2, 25, K=65, P=11, D=6)   # KG = 9, static n = 1..10
+    _run(f, x, 65, 11)
+    f, x = _corpus(rng, 24, [3, 7, 10], 2, 20, K=100, P=9, D=6)           # KG = 13
+    _run(f, x, 100, 9, kind='gaussian')
+
+
+def test_large_phone_inventory_and_long_captions():
+    rng = np.random.default_rng(4)
+    f, x = _corpus(rng, 10, [2, 4], 20, 40, K=20, P=600, D=4)            # P*K*8 = 96 KB phone table
+    _run(f, x, 20, 600, iters=1)
+    f, x = _corpus(rng, 10, [2, 4], 100, 125, K=20, P=12, D=4)           # T up to 125 (12^-125 ~ 1e-135)
+    _run(f, x, 20, 12, iters=1)
+
+
+def test_fp32_feature_storage_matches_fp64():
+    rng = np.random.default_rng(5)
+    f, x = _corpus(rng, 12, [2, 3, 4], 3, 15, K=8, P=6, D=7)             # fp32-representable features
+    _run(f, x, 8, 6, feat_dtype=np.float32)
+
+
+def test_identical_pairs_give_identical_outputs():
+    """Determinism / slot independence: the same pair repeated many times -> identical per-pair rows."""
+    from multimodalworddiscovery_b200.corpus import pack_pairs
+    from multimodalworddiscovery_b200.engine import IKEngine
+    rng = np.random.default_rng(6)
+    f, x = _corpus(rng, 1, [5], 20, 20, K=65, P=9, D=6)
+    feats, phones = f * 37, x * 37
+    p = orc.initial_params(feats, 65, 9, 'linear', W=0.3 * rng.standard_normal((65, 7)), lr=0.1)
+    pk = pack_pairs(feats, phones, feat_dtype=np.float64)
+    outs = []
+    for _ in range(2):
+        eng = IKEngine(pk, 65, 9)
+        eng.set_params(p['init'], p['trans'], p['obs'], p['W'])
+        eng.em_iteration(0.1, 0.0)
+        cC = eng.cC.cpu().numpy().reshape(37, 5, 65)
+        assert np.all(cC == cC[0])
+        outs.append((eng.get_params(), eng.pair_ll.cpu().numpy().copy()))
+    for a, b in zip(outs[0][0], outs[1][0]):       # run-to-run bitwise reproducibility
+        if isinstance(a, dict):
+            for m in a:
+                assert np.array_equal(a[m], b[m])
+        else:
+            assert np.array_equal(a, b)
+    assert np.array_equal(outs[0][1], outs[1][1])
