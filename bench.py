@@ -83,6 +83,13 @@ def make_shard(torch, dev, n_pairs_global, rank, world, variant, seed=20261018):
                 W=W, n_local=len(mine))
 
 
+def flops_per_pair(T_mean, n_mean, n3_mean):
+    """Algorithmic float64 flop per pair: posterior GEMM + recursion and counts
+    + restricted concept chains + gradient GEMM."""
+    K, D = K_CONCEPTS, D_FEAT
+    return 2 * n_mean * K * (D + 1) + 30 * T_mean * n_mean * K + 2 * T_mean * K * n3_mean + 2 * n_mean * K * (D + 1)
+
+
 def bytes_per_pair(T_mean, n_mean):
     """SURVEY 8(d) algorithmic bytes per pair: phones + features + conceptCounts + concept
     alignment argmax + log-likelihood."""
@@ -384,6 +391,16 @@ def gpu_arm(args):
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         achieved = pk.n_pairs * bpp / (kern_ms[dom] * 1e-3) / 1e9
+        n_arr = np.diff(pk.region_off).astype(np.float64)
+        fpp = flops_per_pair(T_mean, n_mean, float(np.mean(n_arr ** 3)))
+        fp64_peak = 37.0          # TFLOP/s, measured: profiles/r01_fp64_peak_microbench.txt
+        traffic = None
+        try:                      # DRAM bytes of the dominant kernel, ncu --set full at this workload
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+            if tr.get('pairs_per_launch') == pk.n_pairs and tr.get('kernel') == dom:
+                traffic = tr['dram_bytes_per_launch']
+        except (OSError, ValueError):
+            pass
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
@@ -396,10 +413,14 @@ def gpu_arm(args):
                             * args.steps * world,
             'kernel_ms_per_step': kern_ms,
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None,
+                         'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650',
                          'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pk.n_pairs,
                          'note': 'path is FP64-pipe bound (SURVEY 8d), see DESIGN.md'},
+            'fp64_roofline': {'bound': 'fp64 pipe (DFMA/DMMA)', 'achieved': args.pairs * fpp / (ms_step * 1e-3) / 1e12 / world,
+                              'peak': fp64_peak, 'unit': 'TFLOP/s per GPU', 'frac': args.pairs * fpp / (ms_step * 1e-3) / 1e12 / world / fp64_peak,
+                              'algorithmic_flop_per_pair': fpp,
+                              'peak_source': 'profiles/r01_fp64_peak_microbench.txt (measured DFMA = DMMA = 37.0)'},
             'cpu_baseline': cpu_baseline,
             'clocks': clock_info,
         }

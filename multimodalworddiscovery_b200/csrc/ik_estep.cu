@@ -124,9 +124,12 @@ ik_estep_kernel(const EstepArgs a) {
   if (TAB)
     for (int e = tid; e < a.P * K; e += blockDim.x) smem[o_tab + e] = 0.0;
 
+  // checkpoint slices are padded to whole 128-byte lines (SL doubles) so that a consumed slice can
+  // be dropped from L2 with discard.global.L2 instead of being written back to HBM
+  const int SL = (n * KS + 15) & ~15;
   double* cta_scr = a.scratch + (size_t)blockIdx.x * a.cta_scratch;
-  double* my_ckpt = cta_scr + ((size_t)slot * a.NC * n + i) * KS + l8;              // + c*n*KS + 8j
-  double* my_hist = cta_scr + (size_t)PP * a.NC * n * KS + (size_t)slot * a.Tmax * n + i;  // + t*n : c_t[i]
+  double* my_ckpt = cta_scr + (size_t)slot * a.NC * SL + i * KS + l8;               // + c*SL + 8j
+  double* my_hist = cta_scr + (size_t)PP * a.NC * SL + (size_t)slot * a.Tmax * n + i;  // + t*n : c_t[i]
   const int buf_row = (slot * B * n + i) * KS + l8;                                  // + tt*n*KS + 8j
   const int nKS = n * KS;
   double* g_phone = a.part_phone + (size_t)blockIdx.x * a.P * K;
@@ -200,7 +203,7 @@ ik_estep_kernel(const EstepArgs a) {
           for (int j = 0; j < KG; ++j) onext[j] = (j < KG - 1 || kv_last) ? __ldg(orow + 8 * j) : 0.0;
         }
         if (t % B == 0 && !a.ll_only) {
-          double* dst = my_ckpt + (size_t)(t / B) * nKS;
+          double* dst = my_ckpt + (size_t)(t / B) * SL;
 #pragma unroll
           for (int j = 0; j < KG; ++j) __stcg(dst + 8 * j, al[j]);
         }
@@ -253,7 +256,7 @@ ik_estep_kernel(const EstepArgs a) {
       const int len = min(B, Tmax - t0);
       __syncthreads();  // column reads of the previous block are complete
       if (t0 < T) {
-        const double* src = my_ckpt + (size_t)c * nKS;
+        const double* src = my_ckpt + (size_t)c * SL;
         double cb[BMAX];
 #pragma unroll
         for (int tt = 1; tt < BMAX; ++tt)
@@ -316,6 +319,17 @@ ik_estep_kernel(const EstepArgs a) {
           }
         }
         __syncthreads();
+        if (tt == len - 1) {
+          // every thread has re-read its part of checkpoint slice c: the slice is dead, drop it
+          const int lines = SL >> 4;
+          for (int ln = tid; ln < PP * lines; ln += blockDim.x) {
+            const int sl = ln / lines, l = ln - sl * lines;
+            if (t0 < s_T[sl]) {
+              const double* dead = cta_scr + ((size_t)sl * a.NC + c) * SL + l * 16;
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead) : "memory");
+            }
+          }
+        }
         // drain the phone-count rows deferred by the previous step: thread k owns column k of
         // the per-CTA table for every slot, so the read-modify-writes never race and their
         // order (t descending, slot ascending) is fixed.
@@ -604,7 +618,8 @@ static EstepPlan plan_bucket(int n, int K, int P, int Tmax, int64_t npairs) {
   if (grid > nquads) grid = nquads;
   if (grid < 1) grid = 1;
   pl.grid = (int)grid;
-  pl.cta_scratch = (int64_t)pl.PP * ((int64_t)pl.NC * n * pl.KS + (int64_t)Tmax * n);
+  const int64_t SL = ((int64_t)n * pl.KS + 15) & ~(int64_t)15;   // 128-byte aligned checkpoint slices
+  pl.cta_scratch = (((int64_t)pl.PP * ((int64_t)pl.NC * SL + (int64_t)Tmax * n)) + 15) & ~(int64_t)15;
   return pl;
 }
 
