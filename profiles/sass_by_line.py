@@ -14,6 +14,10 @@ from collections import defaultdict
 
 def main(sass_csv, lines_txt, kernel, src=None, top=45):
     rows = list(csv.reader(open(sass_csv)))
+    # keep the first kernel section only (a report with several launches repeats the header)
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+    if len(starts) > 1:
+        rows = rows[:starts[1]]
     hdr = rows[1]
     ci = hdr.index('Instructions Executed')
     cs = hdr.index('# Samples')
