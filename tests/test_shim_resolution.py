@@ -18,16 +18,54 @@ def test_driver_star_imports_resolve_to_b200_classes():
 import sys
 sys.path.insert(0, %r)                      # the driver's own directory comes first, like `python run_image2phone.py`
 from hmm_dnn.image_phone_hmm_word_discoverer import *
+from hmm_dnn.image_phone_hmm_dnn_word_discoverer import *      # run_image2phone.py:2 -- not mirrored: reference file
 from hmm_dnn.image_phone_gaussian_hmm_word_discoverer import *
+from hmm_dnn.image_audio_hmm_word_discoverer import *          # run_image2audio.py -- reference file
 from hmm.hmm_word_discoverer import *
+from hmm.audio_segembed_hmm_word_discoverer import *
 from hmm.audio_hmm_word_discoverer import *
 from utils.clusteval import *               # reference module; needs the nltk / matplotlib stubs
 from utils.postprocess import *
-for cls in (ImagePhoneHMMWordDiscoverer, ImagePhoneGaussianHMMWordDiscoverer, HMMWordDiscoverer, AudioHMMWordDiscoverer):
+for cls in (ImagePhoneHMMWordDiscoverer, ImagePhoneGaussianHMMWordDiscoverer, HMMWordDiscoverer, AudioHMMWordDiscoverer,
+            SegEmbedHMMWordDiscoverer):
     assert cls.__module__.startswith('multimodalworddiscovery_b200.'), cls.__module__
+assert ImagePhoneHMMDNNWordDiscoverer.__module__ == 'hmm_dnn.image_phone_hmm_dnn_word_discoverer'
+assert ImageAudioHMMWordDiscoverer.__module__ == 'hmm_dnn.image_audio_hmm_word_discoverer'
 assert np.__name__ == 'numpy' and json.__name__ == 'json'   # names the drivers rely on (run_image2phone.py:132,137)
 print('OK')
 ''' % REF
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'shim'), ROOT]))
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, cwd='/tmp')
     assert out.returncode == 0 and 'OK' in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout not present')
+def test_unchanged_driver_reaches_the_cuda_path(tmp_path):
+    """Run the reference's run_image2phone.py UNCHANGED from a scratch directory laid out as the
+    driver expects (CWD-relative data/mscoco/..., an existing hmm_dnn/exp/).  It must construct the
+    B200 class, print the reference's corpus summary and enter trainUsingEM; without a GPU the
+    engine then fails loudly (no CPU fallback), with a GPU it completes and writes the alignment."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(0)
+    data = tmp_path / 'data' / 'mscoco'
+    data.mkdir(parents=True)
+    (tmp_path / 'hmm_dnn' / 'exp').mkdir(parents=True)
+    feats, caps = {}, []
+    for i in range(6):
+        feats['arr_%d' % i] = rng.standard_normal((int(rng.integers(1, 4)), 16)).astype(np.float32)
+        caps.append(' '.join('p%d' % p for p in rng.integers(0, 7, int(rng.integers(3, 9)))))
+    np.savez(str(data / 'mscoco2k_res34_embed512dim.npz'), **feats)
+    (data / 'mscoco2k_phone_captions.txt').write_text('\n'.join(caps) + '\n')
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'shim'), ROOT]))
+    out = subprocess.run([sys.executable, os.path.join(REF, 'run_image2phone.py'), '--dataset', 'mscoco2k',
+                          '--feat_type', 'res34', '--model_type', 'linear', '--lr', '0.01'],
+                         env=env, capture_output=True, text=True, cwd=str(tmp_path))
+    assert 'Start training the model ...' in out.stdout, out.stderr[-1500:]
+    assert '----- Corpus Summary -----' in out.stdout and 'Number of examples:  6' in out.stdout
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stderr[-1500:]
+        exp = [d for d in (tmp_path / 'hmm_dnn' / 'exp').iterdir()][0]
+        assert (exp / 'image_phone_alignment.json').exists()
+    else:
+        assert out.returncode != 0 and 'MwdError' in out.stderr and 'no CPU fallback' in out.stderr
