@@ -160,9 +160,18 @@ def estep_pair(v, x, params, kind):
     )
 
 
+def hidden_layer(v, V):
+    """hiddenLayer (ReLU), image_phone_hmm_dnn_word_discoverer.py:573-579."""
+    vc = np.concatenate([v, np.ones((v.shape[0], 1))], axis=1)
+    h = vc @ V.T
+    return h * (h > 0.)
+
+
 def posterior(v, params, kind):
     if kind == 'linear':
         return posterior_linear(v, params['W'])
+    if kind == 'two-layer':   # softmaxLayer(hiddenLayer(v)), image_phone_hmm_dnn_word_discoverer.py:310,581-590
+        return posterior_linear(hidden_layer(v, params['V']), params['W'])
     return posterior_gaussian(v, params['mus'], params['width'])
 
 
@@ -196,6 +205,12 @@ def em_iteration(feats, phones, params, kind='linear', update_lr=False, epoch=0)
     new = dict(params)
     new['init'], new['trans'] = {}, {}
     for m in lens:
+        if kind == 'two-layer' and params.get('freeze_trans', False):
+            # image_phone_hmm_dnn_word_discoverer.py:247-273 with freezeTransition=True
+            ic = np.maximum(initC[m], EPS)
+            new['init'][m] = ic / np.sum(ic)
+            new['trans'][m] = params['trans'][m].copy()
+            continue
         if kind == 'linear':
             new['init'][m] = initC[m] / np.sum(initC[m])                      # :240
             tot = np.sum(transC[m], axis=1)                                   # :245
@@ -225,6 +240,22 @@ def em_iteration(feats, phones, params, kind='linear', update_lr=False, epoch=0)
             vc = np.concatenate([v, np.ones((v.shape[0], 1))], axis=1)
             dW += 1.0 / N * (cC - pz).T @ vc
         new['W'] = (1.0 - mom) * params['W'] + lr * dW
+        grad = dW
+    elif kind == 'two-layer':
+        # updateNeuralNetWeights, image_phone_hmm_dnn_word_discoverer.py:504-528
+        Wm, Vm = params['W'], params['V']
+        dW = np.zeros_like(Wm)
+        dV = np.zeros_like(Vm)
+        for v, cC, pz in zip(feats, cC_all, pz_all):
+            h = hidden_layer(v, Vm)
+            Delta = cC - pz
+            Eps = Delta @ Wm[:, :-1]
+            vc = np.concatenate([v, np.ones((v.shape[0], 1))], axis=1)
+            hc = np.concatenate([h, np.ones((h.shape[0], 1))], axis=1)
+            dW += 1.0 / N * Delta.T @ hc
+            dV += 1.0 / N * (Eps * (h > 0)).T @ vc
+        new['W'] = (1.0 - mom) * Wm + lr * dW
+        new['V'] = (1.0 - mom) * Vm + lr * dV
         grad = dW
     else:
         # gaussian updateSoftmaxWeight :488-499 (non-exact branch)
@@ -256,6 +287,9 @@ def initial_params(feats, n_words, n_phones, kind='linear', W=None, mus=None, wi
     )
     if kind == 'linear':
         p['W'] = np.array(W, dtype=float)
+    elif kind == 'two-layer':
+        p['W'] = np.array(W, dtype=float)
+        p['V'] = np.array(mus, dtype=float)        # hidden weights travel in the `mus` slot
     else:
         p['mus'] = np.array(mus, dtype=float)
         p['width'] = width
@@ -265,9 +299,11 @@ def initial_params(feats, n_words, n_phones, kind='linear', W=None, mus=None, wi
 # ----------------------------------------------------------------------------------------------
 # decoding
 # ----------------------------------------------------------------------------------------------
-def align(pz, x, obs, pi, A, floor_norm=False):
+def align(pz, x, obs, pi, A, floor_norm=False, floor_scores=True):
     """align, :543-584 (Viterbi over regions with marginal emissions, EPS score floor).
-    ``floor_norm`` selects the gaussian class's floored alignProbs normaliser (gaussian :583)."""
+    ``floor_norm`` selects the gaussian class's floored alignProbs normaliser (gaussian :583);
+    ``floor_scores=False`` is the two-layer class, which does not floor the scores
+    (image_phone_hmm_dnn_word_discoverer.py:612)."""
     n = pz.shape[0]
     T = len(x)
     onehot = np.zeros((T, obs.shape[1]))
@@ -279,7 +315,9 @@ def align(pz, x, obs, pi, A, floor_norm=False):
     for t in range(1, T):
         cand = np.tile(scores, (n, 1)).T * A * p[t]
         bp[t] = np.argmax(cand, axis=0)
-        scores = np.maximum(np.max(cand, axis=0), EPS)
+        scores = np.max(cand, axis=0)
+        if floor_scores:
+            scores = np.maximum(scores, EPS)
         if floor_norm:
             probs.append((scores / np.sum(np.maximum(scores, EPS))).tolist())
         else:

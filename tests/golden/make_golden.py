@@ -77,7 +77,7 @@ def flatten_tables(lens, tabs):
 
 
 def run_ik_case(name, kind, feats, phones, K, n_iter, seed, lr, momentum=0.0, width=1.0,
-                w_scale=0.5, nonuniform_obs=False):
+                w_scale=0.5, nonuniform_obs=False, hidden_dim=0):
     rng = np.random.default_rng(seed)
     D = feats[0].shape[1]
     with tempfile.TemporaryDirectory() as tmp:
@@ -96,6 +96,20 @@ def run_ik_case(name, kind, feats, phones, K, n_iter, seed, lr, momentum=0.0, wi
             cfg['image_posterior_weights_file'] = os.path.join(tmp, 'w.npz')
             with contextlib.redirect_stdout(io.StringIO()):
                 m = mod.ImagePhoneHMMWordDiscoverer(
+                    os.path.join(tmp, 'caps.txt'), os.path.join(tmp, 'feats.npz'), cfg,
+                    obsProbFile=os.path.join(tmp, 'obs.npy') if nonuniform_obs else None,
+                    modelName=os.path.join(tmp, 'm'))
+            P0 = W0
+        elif kind == 'two-layer':
+            mod = load_ref('hmm_dnn/image_phone_hmm_dnn_word_discoverer.py', 'ref_ik_twolayer')
+            H = hidden_dim
+            V0 = w_scale * rng.standard_normal((H, D + 1))
+            W0 = w_scale * rng.uniform(-1., 1., size=(K, H + 1))
+            np.savez(os.path.join(tmp, 'w.npz'), arr_0=V0[:, :-1], arr_1=V0[:, -1], arr_2=W0[:, :-1], arr_3=W0[:, -1])
+            cfg['image_posterior_weights_file'] = os.path.join(tmp, 'w.npz')
+            cfg['hidden_dim'] = H
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = mod.ImagePhoneHMMDNNWordDiscoverer(
                     os.path.join(tmp, 'caps.txt'), os.path.join(tmp, 'feats.npz'), cfg,
                     obsProbFile=os.path.join(tmp, 'obs.npy') if nonuniform_obs else None,
                     modelName=os.path.join(tmp, 'm'))
@@ -122,6 +136,9 @@ def run_ik_case(name, kind, feats, phones, K, n_iter, seed, lr, momentum=0.0, wi
                    phones=np.concatenate(phones))
         if obs0 is not None:
             out['obs0'] = obs0
+        if kind == 'two-layer':
+            out['hidden0'] = V0
+            out['hidden_dim'] = hidden_dim
         with contextlib.redirect_stdout(io.StringIO()):
             m.initializeModel()
         lens = sorted(m.lenProb)
@@ -136,9 +153,12 @@ def run_ik_case(name, kind, feats, phones, K, n_iter, seed, lr, momentum=0.0, wi
             out['init_%d' % it] = flatten_tables(lens, m.init)
             out['trans_%d' % it] = flatten_tables(lens, m.trans)
             out['obs_%d' % it] = m.obs.copy()
-            out['param_%d' % it] = (m.W if kind == 'linear' else m.mus).copy()
-            out['cC_%d' % it] = np.concatenate(m.conceptCounts, axis=0)
-            out['cA_%d' % it] = np.concatenate(m.conceptCountsA, axis=0)
+            out['param_%d' % it] = (m.mus if kind == 'gaussian' else m.W).copy()
+            if kind == 'two-layer':
+                out['hidden_%d' % it] = m.V.copy()       # the class keeps neither conceptCounts nor conceptCountsA
+            else:
+                out['cC_%d' % it] = np.concatenate(m.conceptCounts, axis=0)
+                out['cA_%d' % it] = np.concatenate(m.conceptCountsA, axis=0)
         out['avg_ll'] = np.array(lls)
         with contextlib.redirect_stdout(io.StringIO()):
             out['final_ll'] = m.computeAvgLogLikelihood()
@@ -147,7 +167,10 @@ def run_ik_case(name, kind, feats, phones, K, n_iter, seed, lr, momentum=0.0, wi
             ali = json.load(f)
         out['alignment'] = np.concatenate([np.array(a['alignment']) for a in ali])
         out['image_concepts'] = np.concatenate([np.array(a['image_concepts']) for a in ali])
-        out['concept_alignment'] = np.concatenate([np.array(a['concept_alignment']) for a in ali])
+        if kind == 'two-layer':
+            out['cluster_probs'] = np.concatenate([np.array(a['cluster_probs']).ravel() for a in ali])
+        else:
+            out['concept_alignment'] = np.concatenate([np.array(a['concept_alignment']) for a in ali])
         out['align_probs'] = np.concatenate([np.array(a['align_probs']).ravel() for a in ali])
         # dense forward / backward of pair 0 under the final parameters (API parity of forward())
         out['fwd0'] = m.forward(m.vCorpus[0], m.aCorpus[0])
@@ -184,6 +207,13 @@ def make_ik():
     f, x = synth_ik_corpus(rng, 28, list(range(1, 11)), 4, 60, K=9, P=12, D=8)
     run_ik_case('mixed_linear', 'linear', f, x, K=9, n_iter=3, seed=7, lr=0.2, nonuniform_obs=True)
     run_ik_case('mixed_gaussian', 'gaussian', f, x, K=9, n_iter=3, seed=8, lr=0.2, width=4.0)
+    # two-layer (ReLU MLP posterior) on the mixed corpus and on the short Toeplitz corpus
+    run_ik_case('mixed_twolayer', 'two-layer', f, x, K=9, n_iter=3, seed=9, lr=0.05, hidden_dim=12,
+                w_scale=0.4, nonuniform_obs=True)
+    rng = np.random.default_rng(20261018)
+    f, x = synth_ik_corpus(rng, 24, [1, 2, 3, 4, 5, 6, 7], 2, 14, K=7, P=9, D=6)
+    run_ik_case('short_twolayer', 'two-layer', f, x, K=7, n_iter=3, seed=10, lr=0.1, momentum=0.05,
+                hidden_dim=150, w_scale=0.3)
 
 
 if __name__ == '__main__':

@@ -7,6 +7,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 IK_CASES = ['tiny_linear', 'tiny_gaussian', 'short_toeplitz_linear', 'short_toeplitz_gaussian',
             'long_floor_linear', 'long_floor_gaussian', 'mixed_linear', 'mixed_gaussian']
+IK_TWOLAYER_CASES = ['mixed_twolayer', 'short_twolayer']
 
 
 def load_ik(case):
@@ -32,6 +33,8 @@ def oracle_params_from_golden(g):
     kw = dict(lr=g['lr'], momentum=g['momentum'], obs=g.get('obs0'))
     if g['kind'] == 'linear':
         return orc.initial_params(g['feats_list'], g['K'], g['P'], 'linear', W=g['param0'], **kw)
+    if g['kind'] == 'two-layer':
+        return orc.initial_params(g['feats_list'], g['K'], g['P'], 'two-layer', W=g['param0'], mus=g['hidden0'], **kw)
     return orc.initial_params(g['feats_list'], g['K'], g['P'], 'gaussian', mus=g['param0'],
                               width=g['width'], **kw)
 
