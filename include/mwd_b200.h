@@ -117,6 +117,28 @@ int mwd_posterior_gaussian(const void* feats, int feat_is_f64, int64_t n_regions
                            const double* mus, double width, int n_concepts, double* w_scratch,
                            double* pz, void* stream);
 
+/* ---- two-layer posterior of ImagePhoneHMMDNNWordDiscoverer -----------------------
+ * hiddenLayer -- hmm_dnn/image_phone_hmm_dnn_word_discoverer.py:573-579:
+ *   hidden[r][h] = relu( feats[r] . V[h][0:D] + V[h][D] )             (V: H x (D+1))
+ * the image posterior is then mwd_posterior_linear(hidden (float64, feat_dim = H), W: K x (H+1)). */
+int mwd_hidden_relu(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
+                    const double* V, int hidden_dim, double* hidden, void* stream);
+/* ReLU back-propagation of updateNeuralNetWeights (:510-511,526):
+ *   eps[r][h] = (hidden[r][h] > 0) * sum_k (concept_counts - pz)[r][k] * W[k][h]              */
+int mwd_backprop_hidden(const double* concept_counts, const double* pz, const double* W,
+                        const double* hidden, int64_t n_regions, int n_concepts, int hidden_dim,
+                        double* eps, void* stream);
+/* grad[m][d] = sum_r (delta - minus)[r][m] * [feats[r], 1][d]   (n_rows_out x (D+1), UNscaled);
+ * `minus` may be NULL.  The two weight gradients of :522-526 are two calls of this
+ * (delta = concept_counts, minus = pz over the hidden activations; delta = eps over the features).
+ * grad_partials [dev]: grad_splits x min(n_rows_out,128) x (D+1) scratch.                      */
+int mwd_outer_grad(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
+                   const double* delta, const double* minus, int n_rows_out, double* grad_partials,
+                   double* grad, void* stream);
+/* param = (1 - momentum) * param + lr * scale * grad   (:527-528, scale = 1/N)                 */
+int mwd_sgd_update(double* param, const double* grad, int64_t elems, double scale, double lr,
+                   double momentum, void* stream);
+
 /* forward + backward + updateInitialCounts + updateTransitionCounts + updateStateCounts +
  * computeAvgLogLikelihood -- image_phone_hmm_word_discoverer.py:276-433, 523-531, and the
  * phoneCounts / conceptCountsA accumulation of trainUsingEM :230-235.
@@ -164,10 +186,14 @@ int mwd_ik_posterior_grad_finish(int n_concepts, int feat_dim, const double* gra
  * in place.  lens[n_lens] [host] are the distinct n of the WHOLE corpus (reference: self.lenProb
  * keys); toeplitz = (n_lens >= 6) pooling of :399-413 is applied here (it is linear, so it
  * commutes with the sums over t and over pairs).  n_pairs_global is len(self.vCorpus).       */
+#define MWD_MSTEP_FLOOR_TABLES 1   /* EPS-floor init/trans counts (gaussian and two-layer classes)   */
+#define MWD_MSTEP_NO_POSTERIOR 2  /* leave posterior_param alone (two-layer: mwd_sgd_update instead)*/
+#define MWD_MSTEP_FREEZE_TRANS 4  /* trainUsingEM(freezeTransition=True) of the two-layer class     */
 typedef struct {
-  int32_t gaussian;          /* 0 linear (W), 1 gaussian (mus)                              */
+  int32_t gaussian;          /* 0 linear (W), 1 gaussian (mus; implies FLOOR_TABLES)        */
   int32_t n_concepts, n_phone_types, feat_dim;
   int32_t n_lens;
+  int32_t flags;             /* MWD_MSTEP_* bits                                            */
   const int32_t* lens;       /* [host]                                                      */
   int32_t toeplitz;
   int64_t n_pairs_global;
@@ -189,7 +215,8 @@ int mwd_ik_mstep(const mwd_ik_mstep_args* a, void* stream);
  *   ap_off           [dev] N+1 int64 (required iff align_probs != NULL)
  *   image_concepts   [dev] R      int32  cluster() argmax
  *   cluster_scores   [dev] R x K doubles or NULL  cluster() scores
- *   floor_norm: 1 = gaussian class's floored alignProbs normaliser (gaussian :583)           */
+ *   floor_norm: bit 0 = floored alignProbs normaliser (gaussian :583, two-layer :622);
+ *               bit 1 = do NOT floor the Viterbi scores (two-layer class, :612)              */
 int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int given_alignment, int32_t* alignment,
                   double* align_probs, const int64_t* ap_off, int32_t* image_concepts,
                   double* cluster_scores, void* stream);

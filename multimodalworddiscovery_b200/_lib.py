@@ -48,7 +48,7 @@ class PartialSizes(C.Structure):
 class IkMstepArgs(C.Structure):
     _fields_ = [
         ('gaussian', C.c_int32), ('n_concepts', C.c_int32), ('n_phone_types', C.c_int32),
-        ('feat_dim', C.c_int32), ('n_lens', C.c_int32), ('lens', C.c_void_p),
+        ('feat_dim', C.c_int32), ('n_lens', C.c_int32), ('flags', C.c_int32), ('lens', C.c_void_p),
         ('toeplitz', C.c_int32), ('n_pairs_global', C.c_int64),
         ('lr', C.c_double), ('momentum', C.c_double), ('width', C.c_double),
         ('counts', C.c_void_p), ('grad', C.c_void_p), ('init', C.c_void_p), ('trans', C.c_void_p),
@@ -90,6 +90,10 @@ SYMBOLS = {
     'mwd_ik_scratch_bytes': (_i64, [C.POINTER(IkProblem)]),
     'mwd_posterior_linear': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp, _vp]),
     'mwd_posterior_gaussian': (_i, [_vp, _i, _i64, _i, _vp, _d, _i, _vp, _vp, _vp]),
+    'mwd_hidden_relu': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp, _vp]),
+    'mwd_backprop_hidden': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
+    'mwd_outer_grad': (_i, [_vp, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    'mwd_sgd_update': (_i, [_vp, _vp, _i64, _d, _d, _d, _vp]),
     'mwd_ik_estep': (_i, [C.POINTER(IkProblem), _vp]),
     'mwd_ik_loglik': (_i, [C.POINTER(IkProblem), _vp]),
     'mwd_ik_partial_sizes': (_i, [_i, _i, C.POINTER(PartialSizes)]),

@@ -96,13 +96,13 @@ __global__ void __launch_bounds__(128) ik_decode_kernel(const DecodeArgs a) {
           if (np_greater(cand, best)) { best = cand; arg = i; }
         }
         s_bp[t * kNMax + j] = (unsigned char)arg;                // :562
-        sc = floor_eps(best);                                    // :564
+        sc = (a.floor_norm & 2) ? best : floor_eps(best);        // :564 (two-layer :612 does not floor)
         next[j] = sc;
       }
       __syncwarp();
       if (ap && j < n) {
         double tot = 0.0;
-        for (int i = 0; i < n; ++i) tot += a.floor_norm ? floor_eps(next[i]) : next[i];
+        for (int i = 0; i < n; ++i) tot += (a.floor_norm & 1) ? floor_eps(next[i]) : next[i];
         ap[(size_t)t * n + j] = sc / tot;                        // :571 / gaussian :583
       }
     }

@@ -57,7 +57,7 @@ int sum_doubles(const double* x, int64_t n, double* blk_scratch, double* out, cu
 // init / trans M-step for one m (one CTA per distinct length)
 struct LensArg { int lens[kNMax + 1]; int n; };
 
-__global__ void mstep_init_trans_kernel(LensArg la, int gaussian, int toeplitz,
+__global__ void mstep_init_trans_kernel(LensArg la, int gaussian, int toeplitz, int freeze_trans,
                                         const double* __restrict__ initC,
                                         const double* __restrict__ transC,
                                         double* __restrict__ init, double* __restrict__ trans) {
@@ -102,10 +102,11 @@ __global__ void mstep_init_trans_kernel(LensArg la, int gaussian, int toeplitz,
     sI = t;
   }
   __syncthreads();
-  for (int e = tid; e < m * m; e += blockDim.x) {
-    int r = e / m;
-    if (sTot[r] != 0.0) to[e] = (gaussian ? floor_eps(sC[e]) : sC[e]) / sTot[r];
-  }
+  if (!freeze_trans)
+    for (int e = tid; e < m * m; e += blockDim.x) {
+      int r = e / m;
+      if (sTot[r] != 0.0) to[e] = (gaussian ? floor_eps(sC[e]) : sC[e]) / sTot[r];
+    }
   if (tid < m) io[tid] = (gaussian ? floor_eps(ic[tid]) : ic[tid]) / sI;
 }
 
@@ -183,10 +184,16 @@ extern "C" int mwd_ik_mstep(const mwd_ik_mstep_args* a, void* stream) {
   const double* phoneC = a->counts;
   const double* initC = a->counts + pe;
   const double* transC = a->counts + pe + ie;
-  mstep_init_trans_kernel<<<a->n_lens, 256, 0, st>>>(la, a->gaussian, a->toeplitz, initC, transC,
+  const int floor_tables = (a->gaussian || (a->flags & MWD_MSTEP_FLOOR_TABLES)) ? 1 : 0;
+  mstep_init_trans_kernel<<<a->n_lens, 256, 0, st>>>(la, floor_tables, a->toeplitz,
+                                                     (a->flags & MWD_MSTEP_FREEZE_TRANS) ? 1 : 0, initC, transC,
                                                      a->init, a->trans);
   mstep_obs_kernel<<<(K + 127) / 128, 128, 0, st>>>(phoneC, P, K, a->obsT);
   const double invN = 1.0 / (double)a->n_pairs_global;
+  if (a->flags & MWD_MSTEP_NO_POSTERIOR) {
+    MWD_CHECK_LAUNCH();
+    return 0;
+  }
   if (a->gaussian) {
     const int64_t elems = (int64_t)K * D;
     const double scale = 1.0 / ((double)a->n_pairs_global * a->width);

@@ -35,10 +35,12 @@ __device__ __forceinline__ double load_feat(const FT* p) { return (double)__ldg(
 // NT*8 concept columns: MT*NT accumulator fragments (2 doubles each).  The next 16-wide chunk of
 // V (raw element type) and W is prefetched into registers while the DMMAs of the current chunk
 // run; the fp32->fp64 conversion happens only when the registers are staged into shared memory.
-template <int NT, int MT, typename FT>
+// EPI 0: + bias, row softmax (image posterior);  EPI 1: + bias, ReLU (hidden layer of the two-layer
+// class, hmm_dnn/image_phone_hmm_dnn_word_discoverer.py:573-579).  ldo = row stride of the output.
+template <int NT, int MT, typename FT, int EPI>
 __global__ void __launch_bounds__(256, (NT * MT <= 18) ? 2 : 1)
 posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* __restrict__ W,
-                 int K, double* __restrict__ pz) {
+                 int K, double* __restrict__ pz, int ldo) {
   constexpr int BM = 64 * MT;
   constexpr int KP = 8 * NT;
   __shared__ double sV[BM * LDS_PAD];
@@ -114,6 +116,24 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
   // epilogue: + bias, exp(x - logsumexp(x)) per row (scipy.special.logsumexp is max-shifted).
   // Fragment layout: lane holds row g4, columns j*8 + l4*2 + {0,1}; the 4 lanes l4=0..3 of a
   // group share the row.
+  if (EPI == 1) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const int64_t gr = row0 + (warp * MT + m) * 8 + g4;
+      if (gr >= R) continue;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int k = j * 8 + l4 * 2 + h;
+          if (k < K) {
+            const double x = acc[m][j][h] + __ldg(W + (size_t)k * ldw + D);
+            pz[gr * ldo + k] = (x > 0.0) ? x : 0.0;
+          }
+        }
+    }
+    return;
+  }
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
     double mx = -INFINITY;
@@ -147,7 +167,7 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           int k = j * 8 + l4 * 2 + h;
-          if (k < K) pz[gr * K + k] = exp(acc[m][j][h] - lse);
+          if (k < K) pz[gr * ldo + k] = exp(acc[m][j][h] - lse);
         }
     }
   }
@@ -175,32 +195,38 @@ __global__ void gaussian_expand_kernel(const double* __restrict__ mus, int K, in
   }
 }
 
-template <int NT>
+template <int NT, int EPI>
 static int launch_posterior(const void* feats, int is64, int64_t R, int D, const double* W, int K,
-                            double* pz, cudaStream_t st) {
+                            double* pz, int ldo, cudaStream_t st) {
   if (R <= 0) return 0;
   constexpr int MT = (NT <= 9) ? 2 : 1;
   int64_t grid = (R + 64 * MT - 1) / (64 * MT);
   MWD_REQUIRE(grid <= 0x7fffffff, "too many regions for one launch");
   if (is64)
-    posterior_kernel<NT, MT, double><<<(unsigned)grid, 256, 0, st>>>((const double*)feats, R, D, W, K, pz);
+    posterior_kernel<NT, MT, double, EPI><<<(unsigned)grid, 256, 0, st>>>((const double*)feats, R, D, W, K, pz, ldo);
   else
-    posterior_kernel<NT, MT, float><<<(unsigned)grid, 256, 0, st>>>((const float*)feats, R, D, W, K, pz);
+    posterior_kernel<NT, MT, float, EPI><<<(unsigned)grid, 256, 0, st>>>((const float*)feats, R, D, W, K, pz, ldo);
   MWD_CHECK_LAUNCH();
   return 0;
 }
 
-static int posterior_dispatch(const void* feats, int is64, int64_t R, int D, const double* W, int K,
-                              double* pz, cudaStream_t st) {
-  MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "n_concepts %d outside [1,%d]", K, MWD_KMAX);
+template <int EPI>
+static int posterior_dispatch_epi(const void* feats, int is64, int64_t R, int D, const double* W, int K,
+                                  double* pz, int ldo, cudaStream_t st) {
+  MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "%d output columns outside [1,%d]", K, MWD_KMAX);
   switch ((K + 7) / 8) {
-#define MWD_NT(T) case T: return launch_posterior<T>(feats, is64, R, D, W, K, pz, st);
+#define MWD_NT(T) case T: return launch_posterior<T, EPI>(feats, is64, R, D, W, K, pz, ldo, st);
     MWD_NT(1) MWD_NT(2) MWD_NT(3) MWD_NT(4) MWD_NT(5) MWD_NT(6) MWD_NT(7) MWD_NT(8)
     MWD_NT(9) MWD_NT(10) MWD_NT(11) MWD_NT(12) MWD_NT(13) MWD_NT(14) MWD_NT(15) MWD_NT(16)
 #undef MWD_NT
   }
-  set_error("n_concepts %d not supported", K);
+  set_error("%d output columns not supported", K);
   return 2;
+}
+
+static int posterior_dispatch(const void* feats, int is64, int64_t R, int D, const double* W, int K,
+                              double* pz, cudaStream_t st) {
+  return posterior_dispatch_epi<0>(feats, is64, R, D, W, K, pz, K, st);
 }
 
 // ------------------------------------------------------------------------------ K4
@@ -216,7 +242,7 @@ constexpr int BR = 16;
 template <int MT8, typename FT>
 __global__ void __launch_bounds__(256, (MT8 <= 9) ? 2 : 1)
 posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* __restrict__ cC,
-                      const double* __restrict__ pz, int K, int64_t rows_per_split,
+                      const double* __restrict__ pz, int ldc, int K, int64_t rows_per_split,
                       double* __restrict__ partial, int accumulate) {
   constexpr int KP = 8 * MT8;
   constexpr int LDD = KP + 4;            // Delta tile [BR][KP], padded: 608 B == 96 mod 128 (KP=72)
@@ -255,8 +281,8 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
       int rr = e / KP, k = e - rr * KP;
       int64_t r = r0 + rr;
       const bool ok = (e < BR * KP && r < rend && k < K);
-      creg[q] = ok ? __ldg(cC + r * K + k) : 0.0;
-      preg[q] = ok ? __ldg(pz + r * K + k) : 0.0;
+      creg[q] = ok ? __ldg(cC + r * ldc + k) : 0.0;
+      preg[q] = (ok && pz) ? __ldg(pz + r * ldc + k) : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < VPT; ++q) {
@@ -331,27 +357,135 @@ __global__ void grad_reduce_kernel(const double* __restrict__ partial, int split
   grad[e] = s;
 }
 
+struct GradIn {
+  const void* feats; int feat_is_f64; int64_t R; int D;
+  const double* delta; const double* minus; int ldc; int K;
+};
+
 template <int MT8>
-static int launch_grad(const mwd_ik_problem* p, double* partial, int accumulate, cudaStream_t st) {
-  const int D = p->feat_dim, K = p->n_concepts;
-  const int64_t R = p->n_regions;
+static int launch_grad(const GradIn& g, double* partial, int accumulate, cudaStream_t st) {
+  const int D = g.D, K = g.K;
+  const int64_t R = g.R;
   int64_t rps = (R + kGradSplits - 1) / kGradSplits;
   rps = ((rps + BR - 1) / BR) * BR;
   if (rps < BR) rps = BR;
   dim3 grid((D + BD - 1) / BD, kGradSplits);
-  if (p->feat_is_f64)
-    posterior_grad_kernel<MT8, double><<<grid, 256, 0, st>>>((const double*)p->feats, R, D,
-                                                             p->concept_counts, p->pz, K, rps, partial, accumulate);
+  if (g.feat_is_f64)
+    posterior_grad_kernel<MT8, double><<<grid, 256, 0, st>>>((const double*)g.feats, R, D, g.delta, g.minus,
+                                                             g.ldc, K, rps, partial, accumulate);
   else
-    posterior_grad_kernel<MT8, float><<<grid, 256, 0, st>>>((const float*)p->feats, R, D,
-                                                            p->concept_counts, p->pz, K, rps, partial, accumulate);
+    posterior_grad_kernel<MT8, float><<<grid, 256, 0, st>>>((const float*)g.feats, R, D, g.delta, g.minus,
+                                                            g.ldc, K, rps, partial, accumulate);
   MWD_CHECK_LAUNCH();
   return 0;
+}
+
+// eps[r][h] = (hidden[r][h] > 0) * sum_k (cC - pz)[r][k] * W[k][h]   (ReLU back-propagation,
+// hmm_dnn/image_phone_hmm_dnn_word_discoverer.py:510-511,526)
+__global__ void backprop_hidden_kernel(const double* __restrict__ cC, const double* __restrict__ pz,
+                                       const double* __restrict__ W, const double* __restrict__ hidden,
+                                       int64_t R, int K, int H, double* __restrict__ eps) {
+  extern __shared__ double s_d[];          // Delta rows of this CTA: [rows][K]
+  const int rows = blockDim.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows;
+  for (int e = threadIdx.y * blockDim.x + threadIdx.x; e < rows * K; e += rows * blockDim.x) {
+    int rr = e / K, k = e - rr * K;
+    int64_t r = r0 + rr;
+    s_d[e] = (r < R) ? (cC[r * K + k] - pz[r * K + k]) : 0.0;
+  }
+  __syncthreads();
+  const int64_t r = r0 + threadIdx.y;
+  if (r >= R) return;
+  const double* d = s_d + threadIdx.y * K;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) acc = fma(d[k], __ldg(W + (size_t)k * (H + 1) + h), acc);
+    eps[r * H + h] = (hidden[r * H + h] > 0.0) ? acc : 0.0;
+  }
+}
+
+__global__ void sgd_update_kernel(const double* __restrict__ grad, int64_t elems, double scale, double lr,
+                                  double momentum, double* __restrict__ param) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  param[e] = (1.0 - momentum) * param[e] + lr * (scale * grad[e]);
 }
 
 }  // namespace mwd
 
 using namespace mwd;
+
+static int grad_generic(const GradIn& g, double* grad_partials, int accumulate, cudaStream_t st) {
+  const int K = g.K;
+  MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "%d gradient rows outside [1,%d]", K, MWD_KMAX);
+  int rc = 2;
+  switch ((K + 7) / 8) {
+#define MWD_MT(T) case T: rc = launch_grad<T>(g, grad_partials, accumulate, st); break;
+    MWD_MT(1) MWD_MT(2) MWD_MT(3) MWD_MT(4) MWD_MT(5) MWD_MT(6) MWD_MT(7) MWD_MT(8)
+    MWD_MT(9) MWD_MT(10) MWD_MT(11) MWD_MT(12) MWD_MT(13) MWD_MT(14) MWD_MT(15) MWD_MT(16)
+#undef MWD_MT
+  }
+  return rc;
+}
+
+static int grad_partials_impl(const mwd_ik_problem* p, double* grad_partials, int accumulate,
+                              cudaStream_t st) {
+  GradIn g{p->feats, p->feat_is_f64, p->n_regions, p->feat_dim, p->concept_counts, p->pz, p->n_concepts,
+           p->n_concepts};
+  return grad_generic(g, grad_partials, accumulate, st);
+}
+
+
+extern "C" int mwd_hidden_relu(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
+                               const double* V, int hidden_dim, double* hidden, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  for (int c0 = 0; c0 < hidden_dim; c0 += MWD_KMAX) {     // column chunks of <= 128 hidden units
+    const int cols = hidden_dim - c0 < MWD_KMAX ? hidden_dim - c0 : MWD_KMAX;
+    int rc = posterior_dispatch_epi<1>(feats, feat_is_f64, n_regions, feat_dim, V + (size_t)c0 * (feat_dim + 1),
+                                       cols, hidden + c0, hidden_dim, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int mwd_backprop_hidden(const double* concept_counts, const double* pz, const double* W,
+                                   const double* hidden, int64_t n_regions, int n_concepts, int hidden_dim,
+                                   double* eps, void* stream) {
+  if (n_regions <= 0) return 0;
+  dim3 block(64, 4);
+  const size_t smem = (size_t)block.y * n_concepts * sizeof(double);
+  backprop_hidden_kernel<<<(unsigned)((n_regions + block.y - 1) / block.y), block, smem, as_stream(stream)>>>(
+      concept_counts, pz, W, hidden, n_regions, n_concepts, hidden_dim, eps);
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mwd_outer_grad(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
+                              const double* delta, const double* minus, int n_rows_out, double* grad_partials,
+                              double* grad, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  const int ld = feat_dim + 1;
+  for (int c0 = 0; c0 < n_rows_out; c0 += MWD_KMAX) {      // row chunks of <= 128 output rows
+    const int rows = n_rows_out - c0 < MWD_KMAX ? n_rows_out - c0 : MWD_KMAX;
+    GradIn g{feats, feat_is_f64, n_regions, feat_dim, delta + c0, minus ? minus + c0 : nullptr, n_rows_out, rows};
+    int rc = grad_generic(g, grad_partials, 0, st);
+    if (rc) return rc;
+    const int64_t elems = (int64_t)rows * ld;
+    grad_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(grad_partials, kGradSplits, elems,
+                                                                        grad + (size_t)c0 * ld);
+    MWD_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int mwd_sgd_update(double* param, const double* grad, int64_t elems, double scale, double lr,
+                              double momentum, void* stream) {
+  sgd_update_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, as_stream(stream)>>>(grad, elems, scale, lr,
+                                                                                    momentum, param);
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
 
 extern "C" int mwd_posterior_linear(const void* feats, int feat_is_f64, int64_t n_regions,
                                     int feat_dim, const double* W, int n_concepts, double* pz,
@@ -369,20 +503,6 @@ extern "C" int mwd_posterior_gaussian(const void* feats, int feat_is_f64, int64_
   gaussian_expand_kernel<<<n_concepts, 128, 0, st>>>(mus, n_concepts, feat_dim, width, w_scratch);
   MWD_CHECK_LAUNCH();
   return posterior_dispatch(feats, feat_is_f64, n_regions, feat_dim, w_scratch, n_concepts, pz, st);
-}
-
-static int grad_partials_impl(const mwd_ik_problem* p, double* grad_partials, int accumulate,
-                              cudaStream_t st) {
-  const int K = p->n_concepts;
-  MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "n_concepts %d outside [1,%d]", K, MWD_KMAX);
-  int rc = 2;
-  switch ((K + 7) / 8) {
-#define MWD_MT(T) case T: rc = launch_grad<T>(p, grad_partials, accumulate, st); break;
-    MWD_MT(1) MWD_MT(2) MWD_MT(3) MWD_MT(4) MWD_MT(5) MWD_MT(6) MWD_MT(7) MWD_MT(8)
-    MWD_MT(9) MWD_MT(10) MWD_MT(11) MWD_MT(12) MWD_MT(13) MWD_MT(14) MWD_MT(15) MWD_MT(16)
-#undef MWD_MT
-  }
-  return rc;
 }
 
 extern "C" int mwd_ik_posterior_grad_partial(const mwd_ik_problem* p, double* grad_partials,

@@ -26,7 +26,7 @@ class IKEngine(object):
     """Holds one rank's packed shard, the model parameters and all workspaces in HBM."""
 
     def __init__(self, packed, n_concepts, n_phone_types, gaussian=False, device=None,
-                 keep_concept_counts_a=True, process_group=None):
+                 keep_concept_counts_a=True, process_group=None, hidden_dim=0):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -41,6 +41,8 @@ class IKEngine(object):
         if not (1 <= self.K <= _lib.KMAX):
             raise ValueError('n_words=%d outside [1,%d]' % (self.K, _lib.KMAX))
         self.gaussian = bool(gaussian)
+        self.H = int(hidden_dim)              # > 0: two-layer (ReLU MLP) image posterior
+        self.two_layer = self.H > 0
         self.D = int(packed.feats.shape[1])
         self.pg = process_group
         self.geom = _lib.geometry()
@@ -65,8 +67,12 @@ class IKEngine(object):
         self.init_t = torch.zeros((NMAX + 1, NMAX), dtype=f64, device=dev)
         self.trans_t = torch.zeros((NMAX + 1, NMAX * NMAX), dtype=f64, device=dev)
         self.obsT = torch.zeros((self.P, self.K), dtype=f64, device=dev)
-        pcols = self.D if self.gaussian else self.D + 1
+        pcols = self.D if self.gaussian else (self.H + 1 if self.two_layer else self.D + 1)
         self.post = torch.zeros((self.K, pcols), dtype=f64, device=dev)
+        if self.two_layer:
+            self.V_t = torch.zeros((self.H, self.D + 1), dtype=f64, device=dev)
+            self.hidden = torch.empty((max(R, 1), self.H), dtype=f64, device=dev)
+            self.eps = torch.empty((max(R, 1), self.H), dtype=f64, device=dev)
         self.w_scratch = torch.zeros((self.K, self.D + 1), dtype=f64, device=dev) if self.gaussian else None
         # per-region / per-pair outputs
         self.pz = torch.empty((max(R, 1), self.K), dtype=f64, device=dev)
@@ -81,11 +87,19 @@ class IKEngine(object):
         self._part_init = self.part[ps.phone_elems:ps.phone_elems + ps.init_elems]
         self._part_trans = self.part[ps.phone_elems + ps.init_elems:]
         self.counts_len = int(self.lib.mwd_ik_counts_len(self.K, self.P))
-        self.grad_len = self.K * (self.D + 1)
-        self.reduced = torch.zeros((self.counts_len + self.grad_len,), dtype=f64, device=dev)
+        if self.two_layer:
+            self.grad_len = self.K * (self.H + 1)
+            self.gradV_len = self.H * (self.D + 1)
+        else:
+            self.grad_len = self.K * (self.D + 1)
+            self.gradV_len = 0
+        self.reduced = torch.zeros((self.counts_len + self.grad_len + self.gradV_len,), dtype=f64, device=dev)
         self.counts = self.reduced[:self.counts_len]
-        self.grad = self.reduced[self.counts_len:]
-        self.grad_partials = torch.empty((self.geom.grad_splits, self.K, self.D + 1), dtype=f64, device=dev)
+        self.grad = self.reduced[self.counts_len:self.counts_len + self.grad_len]
+        self.gradV = self.reduced[self.counts_len + self.grad_len:]
+        gp_rows = max(self.K, min(self.H, _lib.KMAX))
+        gp_cols = max(self.D, self.H) + 1
+        self.grad_partials = torch.empty((self.geom.grad_splits, gp_rows, gp_cols), dtype=f64, device=dev)
         self._lens = np.ascontiguousarray(np.array(packed.lens, dtype=np.int32))
         self.toeplitz = 1 if len(packed.lens) >= 6 else 0     # :399
         self.n_pairs_global = int(packed.n_pairs_global)
@@ -128,8 +142,9 @@ class IKEngine(object):
         return p
 
     # ------------------------------------------------------------------ parameters
-    def set_params(self, init, trans, obs, posterior_param):
-        """init/trans: reference dicts keyed by n; obs: (K, P); posterior_param: W (K, D+1) or mus (K, D)."""
+    def set_params(self, init, trans, obs, posterior_param, hidden_param=None):
+        """init/trans: reference dicts keyed by n; obs: (K, P); posterior_param: W (K, D+1) or mus (K, D)
+        (two-layer: W (K, H+1) and hidden_param V (H, D+1))."""
         torch = self.torch
         it, tt = tables_to_dense(init, trans)
         self.init_t.copy_(torch.from_numpy(it))
@@ -142,6 +157,14 @@ class IKEngine(object):
         if pp.shape != tuple(self.post.shape):
             raise ValueError('posterior parameter shape %s != %s' % (pp.shape, tuple(self.post.shape)))
         self.post.copy_(torch.from_numpy(pp))
+        if self.two_layer:
+            hv = np.ascontiguousarray(np.asarray(hidden_param, dtype=np.float64))
+            if hv.shape != tuple(self.V_t.shape):
+                raise ValueError('hidden weight shape %s != %s' % (hv.shape, tuple(self.V_t.shape)))
+            self.V_t.copy_(torch.from_numpy(hv))
+
+    def get_hidden_param(self):
+        return self.V_t.cpu().numpy().copy()
 
     def get_params(self):
         it = self.init_t.cpu().numpy()
@@ -155,7 +178,12 @@ class IKEngine(object):
         """pz = p(z | v) for every region of the shard (softmaxLayer)."""
         lib, st = self.lib, self._stream()
         R = self.pk.n_regions
-        if self.gaussian:
+        if self.two_layer:
+            _lib.check(lib.mwd_hidden_relu(_ptr(self.feats), self.feat_is_f64, R, self.D, _ptr(self.V_t), self.H,
+                                           _ptr(self.hidden), st))
+            _lib.check(lib.mwd_posterior_linear(_ptr(self.hidden), 1, R, self.H, _ptr(self.post), self.K,
+                                                _ptr(self.pz), st))
+        elif self.gaussian:
             _lib.check(lib.mwd_posterior_gaussian(_ptr(self.feats), self.feat_is_f64, R, self.D,
                                                   _ptr(self.post), float(width), self.K,
                                                   _ptr(self.w_scratch), _ptr(self.pz), st))
@@ -192,8 +220,22 @@ class IKEngine(object):
         timed('ik_estep', lambda: _lib.check(lib.mwd_ik_estep(C.byref(prob), st)))
         timed('ik_concept', lambda: _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st)))
         timed('reduce_counts', lambda: _lib.check(lib.mwd_ik_reduce_counts(C.byref(prob), _ptr(self.counts), st)))
-        timed('posterior_grad', lambda: _lib.check(
-            lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st)))
+        if self.two_layer:
+            timed('posterior_grad', self._two_layer_grads)
+        else:
+            timed('posterior_grad', lambda: _lib.check(
+                lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st)))
+
+    def _two_layer_grads(self):
+        """updateNeuralNetWeights :504-526: dW = (cC - pz)^T [h,1];  dV = ((cC - pz) W * (h>0))^T [v,1]."""
+        lib, st = self.lib, self._stream()
+        R = self.pk.n_regions
+        _lib.check(lib.mwd_outer_grad(_ptr(self.hidden), 1, R, self.H, _ptr(self.cC), _ptr(self.pz), self.K,
+                                      _ptr(self.grad_partials), _ptr(self.grad), st))
+        _lib.check(lib.mwd_backprop_hidden(_ptr(self.cC), _ptr(self.pz), _ptr(self.post), _ptr(self.hidden), R,
+                                           self.K, self.H, _ptr(self.eps), st))
+        _lib.check(lib.mwd_outer_grad(_ptr(self.feats), self.feat_is_f64, R, self.D, _ptr(self.eps), C.c_void_p(0),
+                                      self.H, _ptr(self.grad_partials), _ptr(self.gradV), st))
 
     def kernel_launches_per_iteration(self, n_chunks=None):
         """Kernels of libmwd_b200.so launched by one em_iteration / em_iteration_streamed."""
@@ -208,9 +250,10 @@ class IKEngine(object):
         """Sum [counts | grad] over ranks: all_gather + fixed-rank-order sum (bitwise reproducible)."""
         fixed_order_allreduce(self.reduced, self.pg)
 
-    def mstep(self, lr, momentum, width=1.0):
+    def mstep(self, lr, momentum, width=1.0, freeze_trans=False):
         a = IkMstepArgs()
         a.gaussian = 1 if self.gaussian else 0
+        a.flags = (3 if self.two_layer else 0) | (4 if freeze_trans else 0)   # MWD_MSTEP_* bits
         a.n_concepts, a.n_phone_types, a.feat_dim = self.K, self.P, self.D
         a.n_lens, a.lens = len(self._lens), _np_ptr(self._lens)
         a.toeplitz = self.toeplitz
@@ -220,14 +263,21 @@ class IKEngine(object):
         a.init, a.trans, a.obsT = _ptr(self.init_t), _ptr(self.trans_t), _ptr(self.obsT)
         a.posterior_param = _ptr(self.post)
         _lib.check(self.lib.mwd_ik_mstep(C.byref(a), self._stream()))
+        if self.two_layer:     # W and V by plain gradient steps (:527-528)
+            invN = 1.0 / float(self.n_pairs_global)
+            st = self._stream()
+            _lib.check(self.lib.mwd_sgd_update(_ptr(self.post), _ptr(self.grad), self.grad_len, invN, float(lr),
+                                               float(momentum), st))
+            _lib.check(self.lib.mwd_sgd_update(_ptr(self.V_t), _ptr(self.gradV), self.gradV_len, invN, float(lr),
+                                               float(momentum), st))
 
-    def em_iteration(self, lr, momentum, width=1.0, with_cA=True, timers=None):
+    def em_iteration(self, lr, momentum, width=1.0, with_cA=True, timers=None, freeze_trans=False):
         """One epoch body of trainUsingEM.  Returns the device scalar sum of log-likelihoods
         (over ALL ranks) of the parameters that entered the iteration."""
         self.estep(width, with_cA, timers)
         self.allreduce()
         ll = self.counts[self.counts_len - 1].clone()
-        self.mstep(lr, momentum, width)
+        self.mstep(lr, momentum, width, freeze_trans)
         return ll
 
     # ------------------------------------------------------------------ streamed (host-resident) corpus
@@ -282,6 +332,8 @@ class IKEngine(object):
         phone_off, feats, phones laid out like the device buffers.  Same result as em_iteration
         up to the association order of the chunked gradient partials."""
         torch, lib = self.torch, self.lib
+        if self.two_layer:
+            raise MwdError('em_iteration_streamed does not support the two-layer posterior yet')
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         cs = self._copy_stream
@@ -326,7 +378,11 @@ class IKEngine(object):
         self.mstep(lr, momentum, width)
         return ll
 
-    def decode(self, floor_norm=False, want_probs=True, width=1.0):
+    def _floor_flags(self, floor_norm):
+        # bit 0: floored alignProbs normaliser; bit 1: un-floored Viterbi scores (two-layer class)
+        return (1 if (floor_norm or self.two_layer) else 0) | (2 if self.two_layer else 0)
+
+    def decode(self, floor_norm=False, want_probs=True, width=1.0, want_cluster_scores=False):
         """align + cluster for every pair of the shard under the CURRENT parameters.
         Returns (alignment int32 (Ttot,), image_concepts int32 (R,), align_probs f64 ragged | None)."""
         torch = self.torch
@@ -340,8 +396,13 @@ class IKEngine(object):
             ap_off = torch.from_numpy(off).to(self.device)
             ap = torch.empty((max(int(off[-1]), 1),), dtype=torch.float64, device=self.device)
         prob = self._problem()
-        _lib.check(self.lib.mwd_ik_decode(C.byref(prob), 1 if floor_norm else 0, 0, _ptr(ali), _ptr(ap),
-                                          _ptr(ap_off), _ptr(ic), C.c_void_p(0), self._stream()))
+        cs = None
+        if want_cluster_scores:
+            cs = torch.empty((max(pk.n_regions, 1), self.K), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.mwd_ik_decode(C.byref(prob), self._floor_flags(floor_norm), 0, _ptr(ali), _ptr(ap),
+                                          _ptr(ap_off), _ptr(ic), _ptr(cs), self._stream()))
+        if want_cluster_scores:
+            return ali[:pk.n_phones_total], ic[:pk.n_regions], ap, cs[:pk.n_regions]
         return ali[:pk.n_phones_total], ic[:pk.n_regions], ap
 
     def decode_pair(self, v, x, floor_norm=False, width=1.0, alignment=None):
@@ -359,12 +420,7 @@ class IKEngine(object):
         poff = torch.tensor([0, T], dtype=torch.int32, device=dev)
         pz = torch.empty((n, self.K), dtype=torch.float64, device=dev)
         st = self._stream()
-        if self.gaussian:
-            _lib.check(self.lib.mwd_posterior_gaussian(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
-                                                       float(width), self.K, _ptr(self.w_scratch), _ptr(pz), st))
-        else:
-            _lib.check(self.lib.mwd_posterior_linear(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
-                                                     self.K, _ptr(pz), st))
+        self._posterior_of(v_d, n, pz, width)
         p = IkProblem()
         p.n_pairs, p.n_regions, p.n_phones_total = 1, n, T
         p.feat_dim, p.feat_is_f64, p.n_concepts, p.n_phone_types = self.D, self.feat_is_f64, self.K, self.P
@@ -380,7 +436,7 @@ class IKEngine(object):
         ap_off = torch.tensor([0, T * n], dtype=torch.int64, device=dev)
         ic = torch.empty((n,), dtype=torch.int32, device=dev)
         cs = torch.empty((n, self.K), dtype=torch.float64, device=dev)
-        _lib.check(self.lib.mwd_ik_decode(C.byref(p), 1 if floor_norm else 0, 1 if given else 0, _ptr(ali),
+        _lib.check(self.lib.mwd_ik_decode(C.byref(p), self._floor_flags(floor_norm), 1 if given else 0, _ptr(ali),
                                           _ptr(ap), _ptr(ap_off), _ptr(ic), _ptr(cs), st))
         return (ali.cpu().numpy(), ap.cpu().numpy().reshape(T, n), ic.cpu().numpy(), cs.cpu().numpy())
 
@@ -417,12 +473,19 @@ class IKEngine(object):
         dt = np.float64 if self.feat_is_f64 else np.float32
         v_d = torch.from_numpy(np.ascontiguousarray(v, dtype=dt)).to(self.device)
         out = torch.empty((v.shape[0], self.K), dtype=torch.float64, device=self.device)
-        st = self._stream()
-        if self.gaussian:
-            _lib.check(self.lib.mwd_posterior_gaussian(_ptr(v_d), self.feat_is_f64, v.shape[0], self.D,
-                                                       _ptr(self.post), float(width), self.K,
-                                                       _ptr(self.w_scratch), _ptr(out), st))
-        else:
-            _lib.check(self.lib.mwd_posterior_linear(_ptr(v_d), self.feat_is_f64, v.shape[0], self.D,
-                                                     _ptr(self.post), self.K, _ptr(out), st))
+        self._posterior_of(v_d, v.shape[0], out, width)
         return out.cpu().numpy()
+
+    def _posterior_of(self, v_d, n, out, width=1.0):
+        """softmaxLayer of an arbitrary device feature block under the current parameters."""
+        lib, st = self.lib, self._stream()
+        if self.two_layer:
+            h = self.torch.empty((n, self.H), dtype=self.torch.float64, device=self.device)
+            _lib.check(lib.mwd_hidden_relu(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.V_t), self.H, _ptr(h), st))
+            _lib.check(lib.mwd_posterior_linear(_ptr(h), 1, n, self.H, _ptr(self.post), self.K, _ptr(out), st))
+        elif self.gaussian:
+            _lib.check(lib.mwd_posterior_gaussian(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
+                                                  float(width), self.K, _ptr(self.w_scratch), _ptr(out), st))
+        else:
+            _lib.check(lib.mwd_posterior_linear(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
+                                                self.K, _ptr(out), st))

@@ -61,6 +61,7 @@ def one_hot_to_ids(aSen):
 
 class ImagePhoneHMMBase(object):
     GAUSSIAN = False
+    TWO_LAYER = False
 
     # ------------------------------------------------------------------ corpus
     def _read_features(self, imageFeatFile, limit=None):
@@ -135,7 +136,8 @@ class ImagePhoneHMMBase(object):
             dt = np.float64 if self._feature_dtype == 'float64' else np.float32
             pk = pack_pairs(self.vCorpus, self._phone_ids(), feat_dtype=dt, rank=rank, world=world)
             self._eng = IKEngine(pk, self.nWords, self.audioFeatDim, gaussian=self.GAUSSIAN,
-                                 device=self._device, keep_concept_counts_a=self._keep_cA)
+                                 device=self._device, keep_concept_counts_a=self._keep_cA,
+                                 hidden_dim=(self.hiddenDim if self.TWO_LAYER else 0))
             self._eng_token = token
             self._cA_valid = False
         return self._eng
@@ -151,7 +153,8 @@ class ImagePhoneHMMBase(object):
 
     def _push(self):
         eng = self._engine()
-        eng.set_params(self.init, self.trans, self.obs, self._posterior_param())
+        eng.set_params(self.init, self.trans, self.obs, self._posterior_param(),
+                       self.V if self.TWO_LAYER else None)
         return eng
 
     def _pull(self, eng):
@@ -161,6 +164,8 @@ class ImagePhoneHMMBase(object):
             self.trans[m] = trans[m]
         self.obs = obs
         self._set_posterior_param(post)
+        if self.TWO_LAYER:
+            self.V = eng.get_hidden_param()
 
     def _width(self):
         return float(getattr(self, 'width', 1.))
@@ -210,7 +215,7 @@ class ImagePhoneHMMBase(object):
 
     # ------------------------------------------------------------------ EM
     def trainUsingEM(self, numIterations=20, writeModel=False, warmStart=False, convergenceEpsilon=0.01,
-                     printStatus=True, debug=False):
+                     printStatus=True, debug=False, _freeze_trans=False):
         """:198-266.  The E-step (forward/backward, expected counts, concept posteriors), the
         count reduction and the M-step all run on the GPU; the per-epoch log-likelihood the
         reference computes in a separate pass (:216) is produced by the same forward sweep."""
@@ -236,7 +241,7 @@ class ImagePhoneHMMBase(object):
                     self.printAlignment(self.modelName + '_iter=' + str(epoch) + '_alignment', debug=False,
                                         _zero_concept_alignment=True)
                     maxLikelihood = likelihood
-            ll = eng.em_iteration(self.lr, self.momentum, width)
+            ll = eng.em_iteration(self.lr, self.momentum, width, freeze_trans=_freeze_trans)
             self._cA_valid = True
             if printStatus:
                 likelihood = float(ll) / N

@@ -57,6 +57,11 @@ def write_ik_files(tmp, g):
     if g['kind'] == 'linear':
         np.savez(os.path.join(tmp, 'w.npz'), weight=g['param0'][:, :-1], bias=g['param0'][:, -1])
         cfg['image_posterior_weights_file'] = os.path.join(tmp, 'w.npz')
+    elif g['kind'] == 'two-layer':
+        V0, W0 = g['hidden0'], g['param0']
+        np.savez(os.path.join(tmp, 'w.npz'), arr_0=V0[:, :-1], arr_1=V0[:, -1], arr_2=W0[:, :-1], arr_3=W0[:, -1])
+        cfg['image_posterior_weights_file'] = os.path.join(tmp, 'w.npz')
+        cfg['hidden_dim'] = int(V0.shape[0])
     else:
         np.save(os.path.join(tmp, 'mus.npy'), g['param0'])
         cfg['visual_anchor_file'] = os.path.join(tmp, 'mus.npy')
@@ -76,6 +81,11 @@ def make_model(tmp, g):
                 ImagePhoneHMMWordDiscoverer
             m = ImagePhoneHMMWordDiscoverer(caps, feats, cfg, obsProbFile=extra.get('obs'),
                                             modelName=os.path.join(tmp, 'm'))
+        elif g['kind'] == 'two-layer':
+            from multimodalworddiscovery_b200.hmm_dnn.image_phone_hmm_dnn_word_discoverer import \
+                ImagePhoneHMMDNNWordDiscoverer
+            m = ImagePhoneHMMDNNWordDiscoverer(caps, feats, cfg, obsProbFile=extra.get('obs'),
+                                               modelName=os.path.join(tmp, 'm'))
         else:
             from multimodalworddiscovery_b200.hmm_dnn.image_phone_gaussian_hmm_word_discoverer import \
                 ImagePhoneGaussianHMMWordDiscoverer

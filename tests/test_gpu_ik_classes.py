@@ -91,3 +91,43 @@ def test_train_multi_epoch_and_lr_decay(tmp_path):
     with contextlib.redirect_stdout(io.StringIO()):
         m1.trainUsingEM(10, warmStart=True, printStatus=False)
     assert m1.lr == pytest.approx(lr0 / 10)
+
+
+@pytest.mark.parametrize('case', ['mixed_twolayer', 'short_twolayer'])
+def test_twolayer_class_matches_reference(case, tmp_path):
+    """ImagePhoneHMMDNNWordDiscoverer (run_image2phone.py --model_type two-layer), SURVEY 8(f1)."""
+    g = load_ik(case)
+    tmp = str(tmp_path)
+    m = make_model(tmp, g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.initializeModel()
+    for it in range(g['n_iter']):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.trainUsingEM(1, warmStart=True, printStatus=True)
+        ll = np.load(os.path.join(tmp, 'm_likelihoods.npy'))[0]
+        np.testing.assert_allclose(ll, g['avg_ll'][it], rtol=RTOL)
+        np.testing.assert_allclose(flatten_tables(g['lens'], m.init), g['init_%d' % it], rtol=RTOL)
+        np.testing.assert_allclose(flatten_tables(g['lens'], m.trans), g['trans_%d' % it], rtol=RTOL)
+        np.testing.assert_allclose(m.obs, g['obs_%d' % it], rtol=RTOL)
+        np.testing.assert_allclose(m.W, g['param_%d' % it], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(m.V, g['hidden_%d' % it], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(m.computeAvgLogLikelihood(), float(g['final_ll']), rtol=RTOL)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.printAlignment(os.path.join(tmp, 'ali'))
+        m.printModel(os.path.join(tmp, 'model'))
+    ali = json.load(open(os.path.join(tmp, 'ali.json')))
+    assert set(ali[0].keys()) == {'index', 'image_concepts', 'alignment', 'cluster_probs', 'align_probs', 'is_phoneme'}
+    assert np.array_equal(np.concatenate([a['alignment'] for a in ali]), g['alignment'])
+    assert np.array_equal(np.concatenate([a['image_concepts'] for a in ali]), g['image_concepts'])
+    np.testing.assert_allclose(np.concatenate([np.array(a['align_probs']).ravel() for a in ali]),
+                               g['align_probs'], rtol=1e-8)
+    np.testing.assert_allclose(np.concatenate([np.array(a['cluster_probs']).ravel() for a in ali]),
+                               g['cluster_probs'], rtol=1e-8, atol=1e-300)
+    assert os.path.exists(os.path.join(tmp, 'ali_clusters.txt'))
+    assert os.path.exists(os.path.join(tmp, 'model_hiddenweights.npy'))
+    v0, a0 = m.vCorpus[0], m.aCorpus[0]
+    np.testing.assert_allclose(m.forward(v0, a0), g['fwd0'], rtol=RTOL)
+    np.testing.assert_allclose(m.backward(v0, a0), g['bwd0'], rtol=RTOL)
+    h0 = m.hiddenLayer(v0)
+    assert h0.shape == (v0.shape[0], m.hiddenDim) and np.all(h0 >= 0)
+    np.testing.assert_allclose(m.softmaxLayer(h0).sum(1), 1.0, rtol=1e-12)
