@@ -23,31 +23,10 @@
 //     counts by read-modify-write of a per-CTA table that only this CTA touches, in t order.
 #include <stdlib.h>
 
-#include "mwd_common.cuh"
+#include "ik_estep.cuh"
 
 namespace mwd {
 
-struct EstepArgs {
-  const int32_t* region_off;
-  const int32_t* phone_off;
-  const int32_t* phones;
-  const double* pz;
-  const double* init;    // init[n] row
-  const double* trans;   // trans[n] table, [i*n+j]
-  const double* obsT;
-  double* pair_ll;
-  double* cA_out;        // may be null
-  double* part_phone;    // [grid][P*K]
-  double* part_init;     // [grid][(NMAX+1)*NMAX]
-  double* part_trans;    // [grid][(NMAX+1)*NMAX*NMAX]
-  double* scratch;
-  double* stats;         // [slot_off[N]][4]: per (pair, t): s_t[n], floor-sum[n], xi-diag[n], r_t[n]
-  const int64_t* slot_off;
-  int64_t lo, hi;
-  int64_t cta_scratch;   // doubles per CTA
-  int n, K, P, B, NC, Tmax;
-  int ll_only;           // 1: forward sweep + log-likelihood only
-};
 
 constexpr int NQ = 1;   // exchanged per-row quantity: s_t (forward) / r_t (backward)
 constexpr int BMAX = 8; // max checkpoint interval
@@ -674,6 +653,8 @@ extern "C" int64_t mwd_ik_scratch_bytes(const mwd_ik_problem* p) {
     EstepPlan pl = plan_bucket(p->bucket_n[b], p->n_concepts, p->n_phone_types, p->bucket_tmax[b], np_);
     int64_t bytes = pl.cta_scratch * pl.grid * (int64_t)sizeof(double);
     if (bytes > need) need = bytes;
+    bytes = estep_warp_scratch(p->bucket_n[b], p->n_concepts, p->bucket_tmax[b], np_) * (int64_t)sizeof(double);
+    if (bytes > need) need = bytes;
   }
   return need;
 }
@@ -688,7 +669,14 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     const int64_t lo = p->bucket_lo[b], hi = p->bucket_lo[b + 1];
     if (hi <= lo) continue;
     MWD_REQUIRE(n >= 1 && n <= MWD_NMAX, "bucket %d: n=%d outside [1,%d]", b, n, MWD_NMAX);
+    const int64_t warp_scr = estep_warp_scratch(n, p->n_concepts, p->bucket_tmax[b], hi - lo);
+    const bool use_warp = warp_scr > 0;
     EstepPlan pl = plan_bucket(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo);
+    if (use_warp) {   // the warp-per-pair kernel plans its own launch; only the scratch check applies
+      pl.smem = 0;
+      pl.grid = 1;
+      pl.cta_scratch = warp_scr;
+    }
     MWD_REQUIRE(pl.smem <= 227 * 1024, "estep shared memory %zu exceeds 227 KB (n=%d K=%d T=%d)",
                 pl.smem, n, p->n_concepts, p->bucket_tmax[b]);
     MWD_REQUIRE(ll_only || pl.cta_scratch * pl.grid * (int64_t)sizeof(double) <= p->scratch_bytes,
@@ -724,7 +712,8 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     a.Tmax = p->bucket_tmax[b];
     a.ll_only = ll_only;
     int rc = 0;
-    switch (pl.KG) {
+    if (use_warp) rc = estep_warp_launch(a, st);
+    else switch (pl.KG) {
 #define MWD_KG(G) case G: rc = launch_estep_kg<G>(a, pl, st); break;
       MWD_KG(1) MWD_KG(2) MWD_KG(3) MWD_KG(4) MWD_KG(5) MWD_KG(6) MWD_KG(7) MWD_KG(8)
       MWD_KG(9) MWD_KG(10) MWD_KG(11) MWD_KG(12) MWD_KG(13) MWD_KG(14) MWD_KG(15) MWD_KG(16)

@@ -1,0 +1,366 @@
+// K1w -- warp-per-pair form of the fused forward / backward / expected-count kernel of the
+// (region i, concept k)-state HMM (same reference lines as ik_estep.cu:
+//   hmm_dnn/image_phone_hmm_word_discoverer.py forward :276-304, backward :314-335,
+//   updateStateCounts :426-433, computeAvgLogLikelihood :523-531, phoneCounts / conceptCountsA
+//   :233,:235; the init / transition counts are finished by ik_counts_*_kernel from the row
+//   statistics published here).
+//
+// Why a second kernel: the CTA-per-4-pairs kernel needs one __syncthreads per time step and moves
+// every cross-region quantity through shared memory; ncu shows it bound by the LSU data pipe
+// (60 % busy) and barrier latency, FP64 pipe 19 %.  Here ONE WARP owns one caption-image pair:
+//   * lane = (region i, sub-lane j), LPR = 32 / n lanes per region row, lane owns concepts
+//     k = j + LPR * q (q < KG); the whole (i,k) lattice of a step is 32 x KG registers;
+//   * row sums (s_t, r_t, floor-sum, xi diagonal) are shuffle trees inside the row, the
+//     cross-region coupling c_t = Aoff^T s_t / w_t = Aoff r_t is n broadcast shuffles -- no block
+//     barrier, no shared-memory exchange, warps never wait for each other;
+//   * alpha is checkpointed every B steps to an L2-resident per-warp scratch ([q][lane] layout,
+//     one coalesced 256-byte store per register) and the B-1 slices in between are recomputed
+//     into the warp's private shared-memory block on the way back;
+//   * the only shared-memory transpose left is the column sum  sum_i gamma_t[i][k]  (phone counts,
+//     conceptCountsA): rows are written with a stride == LPR (mod 16) doubles, so both the
+//     row-owner stores and the column-owner loads are bank-conflict free;
+//   * phone counts go to a per-WARP table (L2-resident, fixed warp -> pair map, column k is always
+//     touched by the same lane in t order), so the result is reproducible without atomics.
+#include <stdlib.h>
+
+#include "ik_estep.cuh"
+
+namespace mwd {
+
+constexpr int kWpc = 4;            // warps per CTA
+constexpr int kWarpCtasPerSm = 3;  // 12 warps per SM (register budget 65536 / 384 = 170)
+constexpr int kWBmax = 8;          // max checkpoint interval
+
+constexpr bool is_pow2(int v) { return (v & (v - 1)) == 0; }
+constexpr int pow2_below(int v) { int p = 1; while (p * 2 < v) p *= 2; return p; }   // largest 2^e < v (v >= 2)
+
+// sum over the LPR lanes of a region row; the total is valid in the row's first lane (j == 0)
+template <int LPR>
+__device__ __forceinline__ double row_sum_head(double v, int j) {
+  if constexpr (LPR == 1) {
+    return v;
+  } else if constexpr (is_pow2(LPR)) {
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+  } else {
+    constexpr int P2 = pow2_below(LPR);
+    double u = __shfl_down_sync(0xffffffffu, v, P2);
+    if (j + P2 < LPR) v += u;
+#pragma unroll
+    for (int off = P2 / 2; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+  }
+}
+
+template <int N, int KG>
+__global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kernel(const EstepArgs a) {
+  constexpr int LPR = 32 / N;
+  constexpr int ROWL = N * LPR;                                  // lanes that own lattice rows
+  constexpr int KS0 = LPR * KG;                                  // concepts per row incl. padding
+  constexpr int KS = KS0 + (((LPR - KS0) % 16) + 16) % 16;       // smem row stride == LPR (mod 16)
+  constexpr int SL = KG * 32;                                    // doubles per checkpoint slice
+  constexpr int KC = (KS0 + 31) / 32;                            // columns per lane in the column pass
+  const int K = a.K, B = a.B;
+  const int lane = threadIdx.x & 31;
+  const int wic = threadIdx.x >> 5;
+  const int gw = blockIdx.x * kWpc + wic;
+  const int total_warps = gridDim.x * kWpc;
+  const bool on = lane < ROWL;
+  const int i = on ? lane / LPR : 0;
+  const int j = on ? lane - i * LPR : 0;
+  const bool head = on && j == 0;
+  const bool kv_last = on && (j + LPR * (KG - 1) < K);           // validity of the lane's last concept
+
+  extern __shared__ double smem[];
+  double* buf = smem + (size_t)wic * B * (N * KS);               // [B][N][KS] alpha / gamma block
+  double* my_buf = buf + i * KS + j;                             // + tt*N*KS + LPR*q
+
+  const double d_i = a.trans[i * N + i];
+  const double pi_i = a.init[i];
+  double acol[N], arow[N];                                       // Aoff[:, i] and Aoff[i, :]
+#pragma unroll
+  for (int jp = 0; jp < N; ++jp) {
+    acol[jp] = (jp == i) ? 0.0 : a.trans[jp * N + i];
+    arow[jp] = (jp == i) ? 0.0 : a.trans[i * N + jp];
+  }
+
+  double* scr = a.scratch + (size_t)gw * a.cta_scratch;          // [NC][SL] checkpoints, [Tmax][N] c_t
+  double* my_ckpt = scr + lane;                                  // + c*SL + 32*q
+  double* hist = scr + (size_t)a.NC * SL + i;                    // + t*N
+  double* tab = a.part_phone + (size_t)gw * a.P * K;
+  const double* obs_j = a.obsT + j;                              // + x*K + LPR*q
+
+  for (int64_t pair = a.lo + gw; pair < a.hi; pair += total_warps) {
+    const int64_t p0 = a.phone_off[pair];
+    const int T = a.phone_off[pair + 1] - (int32_t)p0;
+    const int64_t r0 = a.region_off[pair];
+    const int32_t* ph = a.phones + p0;
+    double* st = a.stats + 4 * a.slot_off[pair] + i;             // + (t*4 + q)*N
+    if (T <= 0) continue;
+
+    double pz[KG];
+    {
+      const double* prow = a.pz + (r0 + i) * K + j;
+#pragma unroll
+      for (int q = 0; q < KG; ++q) pz[q] = (q < KG - 1 ? on : kv_last) ? prow[LPR * q] : 0.0;
+    }
+
+    // ------------------------------------------------------------------ forward sweep
+    double al[KG];
+    int xn = 0;
+    {
+      const double* orow = obs_j + ph[0] * K;
+#pragma unroll
+      for (int q = 0; q < KG; ++q) {
+        const double o = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
+        al[q] = (pi_i * pz[q]) * o;
+      }
+      if (T > 1) xn = ph[1];
+    }
+    double inorm = 0.0;
+    int to_ckpt = 0;     // steps until the next checkpoint
+    int cidx = 0;
+    for (int t = 0; t < T; ++t) {
+      double onext[KG];
+      if (t + 1 < T) {   // next step's emissions, issued before the reductions
+        const double* orow = obs_j + xn * K;
+#pragma unroll
+        for (int q = 0; q < KG; ++q) onext[q] = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
+        if (t + 2 < T) xn = ph[t + 2];
+      }
+      if (!a.ll_only) {
+        if (to_ckpt == 0) {
+          double* dst = my_ckpt + (size_t)cidx * SL;
+#pragma unroll
+          for (int q = 0; q < KG; ++q) __stcg(dst + 32 * q, al[q]);
+          to_ckpt = B;
+          ++cidx;
+        }
+        --to_ckpt;
+      }
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < KG; ++q) s += al[q];
+      s = row_sum_head<LPR>(s, j);
+      double sv[N];
+#pragma unroll
+      for (int jp = 0; jp < N; ++jp) sv[jp] = __shfl_sync(0xffffffffu, s, jp * LPR);
+      if (t == T - 1) {
+        double L = 0.0;
+#pragma unroll
+        for (int jp = 0; jp < N; ++jp) L += sv[jp];
+        L = floor_eps(L);
+        if (lane == 0) a.pair_ll[pair] = log(L);                       // :529
+        // sum_{i,k} alpha_t beta_t equals the sentence likelihood at every t, so the floored
+        // normaliser of updateStateCounts (:430) is one constant per pair
+        inorm = 1.0 / L;
+      } else {
+        double c = 0.0;
+#pragma unroll
+        for (int jp = 0; jp < N; ++jp) c = fma(acol[jp], sv[jp], c);
+        if (head && !a.ll_only) {
+          __stcg(hist + t * N, c);
+          __stcg(st + (t * 4 + 0) * N, s);
+        }
+#pragma unroll
+        for (int q = 0; q < KG; ++q) al[q] = onext[q] * fma(d_i, al[q], c * pz[q]);
+      }
+    }
+    if (a.ll_only) continue;
+
+    // ------------------------------------------------------------------ backward sweep
+    double bo[KG];          // beta_{t+1} * o_{t+1}
+#pragma unroll
+    for (int q = 0; q < KG; ++q) bo[q] = 0.0;
+    double w = 0.0;         // (Aoff r_{t+1})[i]
+    const int nblk = (T + B - 1) / B;
+    int xb = ph[T - 1];     // phone of the step about to be processed
+    for (int c = nblk - 1; c >= 0; --c) {
+      const int t0 = c * B;
+      const int len = min(B, T - t0);
+      __syncwarp();         // column reads of the previous block are complete
+      {
+        const double* src = my_ckpt + (size_t)c * SL;
+#pragma unroll
+        for (int q = 0; q < KG; ++q) al[q] = __ldcg(src + 32 * q);
+        if (on) {
+#pragma unroll
+          for (int q = 0; q < KG; ++q) my_buf[LPR * q] = al[q];
+        }
+        for (int tt = 1; tt < len; ++tt) {
+          const double cb = __ldcg(hist + (t0 + tt - 1) * N);
+          const double* orow = obs_j + ph[t0 + tt] * K;
+          double* dst = my_buf + tt * (N * KS);
+#pragma unroll
+          for (int q = 0; q < KG; ++q) {
+            const double o = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
+            al[q] = o * fma(d_i, al[q], cb * pz[q]);
+            if (on) dst[LPR * q] = al[q];
+          }
+        }
+      }
+      for (int tt = len - 1; tt >= 0; --tt) {
+        const int t = t0 + tt;
+        const int x = xb;
+        if (t > 0) xb = ph[t - 1];
+        const bool last = (t == T - 1);
+        // phone-count cells of this step (column owner = lane, fixed), loaded early
+        double tabv[KC];
+        double* trow = tab + x * K + lane;
+#pragma unroll
+        for (int m = 0; m < KC; ++m) tabv[m] = (lane + 32 * m < K) ? __ldcg(trow + 32 * m) : 0.0;
+        const double* orow = obs_j + x * K;
+        double* row = my_buf + tt * (N * KS);
+        double sumF = 0.0, dg = 0.0, rr = 0.0;
+#pragma unroll
+        for (int q = 0; q < KG; ++q) {
+          const bool kv = (q < KG - 1) ? on : kv_last;
+          const double av = row[LPR * q];
+          const double beta = last ? 1.0 : fma(d_i, bo[q], w);
+          dg = fma(av, bo[q], dg);
+          const double g = av * beta;
+          sumF += kv ? floor_eps(g) : 0.0;
+          const double o = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
+          bo[q] = beta * o;
+          rr = fma(bo[q], pz[q], rr);
+          if (on) row[LPR * q] = g;
+        }
+        dg *= d_i;
+        __syncwarp();       // gamma slice visible to the column owners
+        // column loads first, the row reductions overlap their latency
+        const double* col = buf + tt * (N * KS) + lane;
+        double cs[KC];
+#pragma unroll
+        for (int m = 0; m < KC; ++m) {
+          cs[m] = 0.0;
+          if (lane + 32 * m < K) {
+#pragma unroll
+            for (int ii = 0; ii < N; ++ii) cs[m] += col[ii * KS + 32 * m];
+          }
+        }
+        sumF = row_sum_head<LPR>(sumF, j);
+        dg = row_sum_head<LPR>(dg, j);
+        rr = row_sum_head<LPR>(rr, j);
+        if (head) {         // row statistics of this step for the count post-pass
+          __stcg(st + (t * 4 + 1) * N, sumF);
+          __stcg(st + (t * 4 + 2) * N, dg);
+          __stcg(st + (t * 4 + 3) * N, rr);
+        }
+        double wn = 0.0;
+#pragma unroll
+        for (int jp = 0; jp < N; ++jp) wn = fma(arow[jp], __shfl_sync(0xffffffffu, rr, jp * LPR), wn);
+        w = wn;
+        // conceptCountsA[t][k] = sum_i gamma_t[i][k]; phoneCounts[k][x_t] += ...  (:430,:233,:235)
+#pragma unroll
+        for (int m = 0; m < KC; ++m) {
+          if (lane + 32 * m < K) {
+            const double v = cs[m] * inorm;
+            __stcg(trow + 32 * m, tabv[m] + v);
+            if (a.cA_out) a.cA_out[(p0 + t) * K + lane + 32 * m] = v;
+          }
+        }
+      }
+      // checkpoint slice c is dead: drop it from L2 instead of letting it be written back
+      for (int ln = lane; ln < SL / 16; ln += 32) {
+        const double* dead = scr + (size_t)c * SL + ln * 16;
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead) : "memory");
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct WarpPlan {
+  int KG, B, NC, grid;
+  size_t smem;
+  int64_t warp_scratch;   // doubles per warp
+};
+
+// (n, KG) instantiations: K = 65 (MSCOCO, run_image2phone.py:43) and K = 50 / 100 (Flickr30k,
+// run_image2phone.py:73 / image_phone_hmm_word_discoverer.py:735) for the n they are fast for.
+#define MWD_WARP_COMBOS(X)                                                              \
+  X(1, 2) X(1, 3) X(1, 4) X(2, 4) X(2, 5) X(2, 7) X(3, 5) X(3, 7) X(3, 10) X(4, 7) X(4, 9) \
+  X(4, 13) X(5, 9) X(5, 11) X(6, 10) X(6, 13)
+
+static int warp_kg(int n, int K) {
+  const int lpr = 32 / n;
+  return (K + lpr - 1) / lpr;
+}
+
+static bool warp_combo(int n, int KG) {
+#define X(NN, GG) if (n == NN && KG == GG) return true;
+  MWD_WARP_COMBOS(X)
+#undef X
+  return false;
+}
+
+static bool warp_enabled() {
+  const char* e = getenv("MWD_ESTEP_WARP");
+  return !(e && atoi(e) == 0);
+}
+
+static bool plan_warp(int n, int K, int Tmax, int64_t npairs, WarpPlan* pl) {
+  if (n < 1 || n > 6 || !warp_enabled()) return false;
+  const int lpr = 32 / n;
+  pl->KG = warp_kg(n, K);
+  if (!warp_combo(n, pl->KG)) return false;
+  const int ks0 = lpr * pl->KG;
+  const int ks = ks0 + (((lpr - ks0) % 16) + 16) % 16;
+  const size_t slice = (size_t)kWpc * n * ks * sizeof(double);     // one alpha slice of every warp of a CTA
+  const size_t budget = (size_t)224 * 1024 / kWarpCtasPerSm - 1024;
+  int B = (int)(budget / slice);
+  if (const char* e = getenv("MWD_ESTEPW_B")) { int v = atoi(e); if (v >= 1 && v < B) B = v; }
+  if (B > kWBmax) B = kWBmax;
+  if (B > Tmax) B = Tmax > 0 ? Tmax : 1;
+  if (B < 2 && Tmax > 1) return false;
+  pl->B = B;
+  pl->NC = (Tmax + B - 1) / B;
+  if (pl->NC < 1) pl->NC = 1;
+  pl->smem = (size_t)B * slice;
+  int64_t grid = (int64_t)sm_count() * kWarpCtasPerSm;
+  const int64_t need = (npairs + kWpc - 1) / kWpc;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  if (grid * kWpc > estep_grid_rows()) return false;
+  pl->grid = (int)grid;
+  pl->warp_scratch = (((int64_t)pl->NC * pl->KG * 32 + (int64_t)Tmax * n) + 15) & ~(int64_t)15;
+  return true;
+}
+
+bool estep_warp_supported(int n, int K) {
+  WarpPlan pl;
+  return plan_warp(n, K, 64, 1 << 20, &pl);
+}
+
+int64_t estep_warp_scratch(int n, int K, int Tmax, int64_t npairs) {
+  WarpPlan pl;
+  if (!plan_warp(n, K, Tmax, npairs, &pl)) return 0;
+  return pl.warp_scratch * pl.grid * kWpc;
+}
+
+template <int N, int KG>
+static int launch_warp(const EstepArgs& a, const WarpPlan& pl, cudaStream_t st) {
+  auto kern = ik_estep_warp_kernel<N, KG>;
+  MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  kern<<<pl.grid, kWpc * 32, pl.smem, st>>>(a);
+  MWD_CHECK_LAUNCH();
+  return 0;
+}
+
+int estep_warp_launch(EstepArgs a, cudaStream_t st) {
+  WarpPlan pl;
+  MWD_REQUIRE(plan_warp(a.n, a.K, a.Tmax, a.hi - a.lo, &pl), "warp E-step: unsupported (n=%d, K=%d)", a.n, a.K);
+  a.B = pl.B;
+  a.NC = pl.NC;
+  a.cta_scratch = pl.warp_scratch;
+#define X(NN, GG) if (a.n == NN && pl.KG == GG) return launch_warp<NN, GG>(a, pl, st);
+  MWD_WARP_COMBOS(X)
+#undef X
+  set_error("warp E-step: no instantiation for (n=%d, KG=%d)", a.n, pl.KG);
+  return 2;
+}
+
+}  // namespace mwd
