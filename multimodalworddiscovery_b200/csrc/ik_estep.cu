@@ -653,7 +653,7 @@ extern "C" int64_t mwd_ik_scratch_bytes(const mwd_ik_problem* p) {
     EstepPlan pl = plan_bucket(p->bucket_n[b], p->n_concepts, p->n_phone_types, p->bucket_tmax[b], np_);
     int64_t bytes = pl.cta_scratch * pl.grid * (int64_t)sizeof(double);
     if (bytes > need) need = bytes;
-    bytes = estep_warp_scratch(p->bucket_n[b], p->n_concepts, p->bucket_tmax[b], np_) * (int64_t)sizeof(double);
+    bytes = estep_warp_scratch(p->bucket_n[b], p->n_concepts, p->n_phone_types, p->bucket_tmax[b], np_) * (int64_t)sizeof(double);
     if (bytes > need) need = bytes;
   }
   return need;
@@ -669,7 +669,7 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     const int64_t lo = p->bucket_lo[b], hi = p->bucket_lo[b + 1];
     if (hi <= lo) continue;
     MWD_REQUIRE(n >= 1 && n <= MWD_NMAX, "bucket %d: n=%d outside [1,%d]", b, n, MWD_NMAX);
-    const int64_t warp_scr = estep_warp_scratch(n, p->n_concepts, p->bucket_tmax[b], hi - lo);
+    const int64_t warp_scr = estep_warp_scratch(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo);
     const bool use_warp = warp_scr > 0;
     EstepPlan pl = plan_bucket(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo);
     if (use_warp) {   // the warp-per-pair kernel plans its own launch; only the scratch check applies

@@ -30,8 +30,8 @@ struct EstepArgs {
 
 // Warp-per-pair kernel (ik_estep_warp.cu).  estep_warp_supported: true when an instantiation exists
 // for (n, K); estep_warp_scratch: doubles of checkpoint scratch the launch needs for this bucket.
-bool estep_warp_supported(int n, int K);
-int64_t estep_warp_scratch(int n, int K, int Tmax, int64_t npairs);
+bool estep_warp_supported(int n, int K, int P);
+int64_t estep_warp_scratch(int n, int K, int P, int Tmax, int64_t npairs);
 int estep_warp_launch(EstepArgs a, cudaStream_t st);
 
 }  // namespace mwd

@@ -53,7 +53,12 @@ __device__ __forceinline__ double row_sum_head(double v, int j) {
   }
 }
 
-template <int N, int KG>
+// OBS_S: the emission table obsT (P x K doubles) is staged in shared memory once per CTA (the L1
+// left beside a large shared-memory carve-out is too small to keep it resident).
+// RB ("register block"): the checkpoint interval is fixed to 2 and the one recomputed alpha slice
+// stays in registers, so alpha never touches shared memory (only the gamma slice does, for the
+// column sums) and o_{t+1} is loaded once for the recompute and the backward step.
+template <int N, int KG, bool OBS_S, bool RB>
 __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kernel(const EstepArgs a) {
   constexpr int LPR = 32 / N;
   constexpr int ROWL = N * LPR;                                  // lanes that own lattice rows
@@ -61,7 +66,8 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
   constexpr int KS = KS0 + (((LPR - KS0) % 16) + 16) % 16;       // smem row stride == LPR (mod 16)
   constexpr int SL = KG * 32;                                    // doubles per checkpoint slice
   constexpr int KC = (KS0 + 31) / 32;                            // columns per lane in the column pass
-  const int K = a.K, B = a.B;
+  const int K = a.K;
+  const int B = RB ? 2 : a.B;
   const int lane = threadIdx.x & 31;
   const int wic = threadIdx.x >> 5;
   const int gw = blockIdx.x * kWpc + wic;
@@ -73,23 +79,30 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
   const bool kv_last = on && (j + LPR * (KG - 1) < K);           // validity of the lane's last concept
 
   extern __shared__ double smem[];
-  double* buf = smem + (size_t)wic * B * (N * KS);               // [B][N][KS] alpha / gamma block
+  const int obs_elems = OBS_S ? ((a.P * K + 1) & ~1) : 0;
+  // per warp: [B][N][KS] alpha / gamma block (RB: two gamma slices used alternately)
+  double* buf = smem + obs_elems + (size_t)wic * B * (N * KS);
+  if (OBS_S) {
+    for (int e = threadIdx.x; e < a.P * K; e += blockDim.x) smem[e] = a.obsT[e];
+    __syncthreads();
+  }
   double* my_buf = buf + i * KS + j;                             // + tt*N*KS + LPR*q
 
   const double d_i = a.trans[i * N + i];
   const double pi_i = a.init[i];
-  double acol[N], arow[N];                                       // Aoff[:, i] and Aoff[i, :]
-#pragma unroll
-  for (int jp = 0; jp < N; ++jp) {
-    acol[jp] = (jp == i) ? 0.0 : a.trans[jp * N + i];
-    arow[jp] = (jp == i) ? 0.0 : a.trans[i * N + jp];
-  }
 
   double* scr = a.scratch + (size_t)gw * a.cta_scratch;          // [NC][SL] checkpoints, [Tmax][N] c_t
   double* my_ckpt = scr + lane;                                  // + c*SL + 32*q
   double* hist = scr + (size_t)a.NC * SL + i;                    // + t*N
   double* tab = a.part_phone + (size_t)gw * a.P * K;
-  const double* obs_j = a.obsT + j;                              // + x*K + LPR*q
+  const double* obs_j = (OBS_S ? smem : a.obsT) + j;             // + x*K + LPR*q
+
+  auto load_obs = [&](double (&o)[KG], int x) {
+    const double* orow = obs_j + x * K;
+#pragma unroll
+    for (int q = 0; q < KG; ++q)
+      o[q] = (q < KG - 1 || kv_last) ? (OBS_S ? orow[LPR * q] : __ldg(orow + LPR * q)) : 0.0;
+  };
 
   for (int64_t pair = a.lo + gw; pair < a.hi; pair += total_warps) {
     const int64_t p0 = a.phone_off[pair];
@@ -108,163 +121,220 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
 
     // ------------------------------------------------------------------ forward sweep
     double al[KG];
-    int xn = 0;
-    {
-      const double* orow = obs_j + ph[0] * K;
-#pragma unroll
-      for (int q = 0; q < KG; ++q) {
-        const double o = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
-        al[q] = (pi_i * pz[q]) * o;
-      }
-      if (T > 1) xn = ph[1];
-    }
     double inorm = 0.0;
-    int to_ckpt = 0;     // steps until the next checkpoint
-    int cidx = 0;
-    for (int t = 0; t < T; ++t) {
-      double onext[KG];
-      if (t + 1 < T) {   // next step's emissions, issued before the reductions
-        const double* orow = obs_j + xn * K;
+    {
+      double acol[N];                                            // Aoff[:, i]
 #pragma unroll
-        for (int q = 0; q < KG; ++q) onext[q] = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
-        if (t + 2 < T) xn = ph[t + 2];
+      for (int jp = 0; jp < N; ++jp) acol[jp] = (jp == i) ? 0.0 : a.trans[jp * N + i];
+      int xn = 0;
+      {
+        double o[KG];
+        load_obs(o, ph[0]);
+#pragma unroll
+        for (int q = 0; q < KG; ++q) al[q] = (pi_i * pz[q]) * o[q];
+        if (T > 1) xn = ph[1];
       }
-      if (!a.ll_only) {
-        if (to_ckpt == 0) {
-          double* dst = my_ckpt + (size_t)cidx * SL;
-#pragma unroll
-          for (int q = 0; q < KG; ++q) __stcg(dst + 32 * q, al[q]);
-          to_ckpt = B;
-          ++cidx;
+      int to_ckpt = 0;     // steps until the next checkpoint
+      int cidx = 0;
+      for (int t = 0; t < T; ++t) {
+        double onext[KG];
+        if (t + 1 < T) {   // next step's emissions, issued before the reductions
+          load_obs(onext, xn);
+          if (t + 2 < T) xn = ph[t + 2];
         }
-        --to_ckpt;
-      }
-      double s = 0.0;
+        if (!a.ll_only) {
+          if (to_ckpt == 0) {
+            double* dst = my_ckpt + (size_t)cidx * SL;
 #pragma unroll
-      for (int q = 0; q < KG; ++q) s += al[q];
-      s = row_sum_head<LPR>(s, j);
-      double sv[N];
-#pragma unroll
-      for (int jp = 0; jp < N; ++jp) sv[jp] = __shfl_sync(0xffffffffu, s, jp * LPR);
-      if (t == T - 1) {
-        double L = 0.0;
-#pragma unroll
-        for (int jp = 0; jp < N; ++jp) L += sv[jp];
-        L = floor_eps(L);
-        if (lane == 0) a.pair_ll[pair] = log(L);                       // :529
-        // sum_{i,k} alpha_t beta_t equals the sentence likelihood at every t, so the floored
-        // normaliser of updateStateCounts (:430) is one constant per pair
-        inorm = 1.0 / L;
-      } else {
-        double c = 0.0;
-#pragma unroll
-        for (int jp = 0; jp < N; ++jp) c = fma(acol[jp], sv[jp], c);
-        if (head && !a.ll_only) {
-          __stcg(hist + t * N, c);
-          __stcg(st + (t * 4 + 0) * N, s);
+            for (int q = 0; q < KG; ++q) __stcg(dst + 32 * q, al[q]);
+            to_ckpt = B;
+            ++cidx;
+          }
+          --to_ckpt;
         }
+        double s = 0.0, s_b = 0.0;
 #pragma unroll
-        for (int q = 0; q < KG; ++q) al[q] = onext[q] * fma(d_i, al[q], c * pz[q]);
+        for (int q = 0; q < KG; ++q) {
+          if (q & 1) s_b += al[q];
+          else s += al[q];
+        }
+        s = row_sum_head<LPR>(s + s_b, j);
+        double sv[N];
+#pragma unroll
+        for (int jp = 0; jp < N; ++jp) sv[jp] = __shfl_sync(0xffffffffu, s, jp * LPR);
+        if (t == T - 1) {
+          double L = 0.0;
+#pragma unroll
+          for (int jp = 0; jp < N; ++jp) L += sv[jp];
+          L = floor_eps(L);
+          if (lane == 0) a.pair_ll[pair] = log(L);                       // :529
+          // sum_{i,k} alpha_t beta_t equals the sentence likelihood at every t, so the floored
+          // normaliser of updateStateCounts (:430) is one constant per pair
+          inorm = 1.0 / L;
+        } else {
+          double c = 0.0;
+#pragma unroll
+          for (int jp = 0; jp < N; ++jp) c = fma(acol[jp], sv[jp], c);
+          if (head && !a.ll_only) {
+            __stcg(hist + t * N, c);
+            __stcg(st + (t * 4 + 0) * N, s);
+          }
+#pragma unroll
+          for (int q = 0; q < KG; ++q) al[q] = onext[q] * fma(d_i, al[q], c * pz[q]);
+        }
       }
     }
     if (a.ll_only) continue;
 
     // ------------------------------------------------------------------ backward sweep
+    double arow[N];                                              // Aoff[i, :]
+#pragma unroll
+    for (int jp = 0; jp < N; ++jp) arow[jp] = (jp == i) ? 0.0 : a.trans[i * N + jp];
     double bo[KG];          // beta_{t+1} * o_{t+1}
 #pragma unroll
     for (int q = 0; q < KG; ++q) bo[q] = 0.0;
-    double w = 0.0;         // (Aoff r_{t+1})[i]
-    const int nblk = (T + B - 1) / B;
-    int xb = ph[T - 1];     // phone of the step about to be processed
-    for (int c = nblk - 1; c >= 0; --c) {
-      const int t0 = c * B;
-      const int len = min(B, T - t0);
-      __syncwarp();         // column reads of the previous block are complete
-      {
-        const double* src = my_ckpt + (size_t)c * SL;
+    double w = 1.0;         // (Aoff r_{t+1})[i]; with bo = 0 the first step gets beta_{T-1} = fma(d, 0, 1) = 1
+
+    // one backward step: alpha_t in av, emissions o_t in o; gamma slice goes to gslice (shared)
+    auto bwd_step = [&](int t, int x, const double (&av)[KG], const double (&o)[KG], double* gslice) {
+      // phone-count cells of this step (column owner = lane, fixed), loaded early
+      double tabv[KC];
+      double* trow = tab + x * K + lane;
 #pragma unroll
-        for (int q = 0; q < KG; ++q) al[q] = __ldcg(src + 32 * q);
-        if (on) {
+      for (int m = 0; m < KC; ++m) tabv[m] = (lane + 32 * m < K) ? __ldcg(trow + 32 * m) : 0.0;
+      double* grow = gslice + i * KS + j;
+      double sumF = 0.0, dg = 0.0, rr = 0.0, sumF_b = 0.0, dg_b = 0.0, rr_b = 0.0;   // two chains each
 #pragma unroll
-          for (int q = 0; q < KG; ++q) my_buf[LPR * q] = al[q];
+      for (int q = 0; q < KG; ++q) {
+        const bool kv = (q < KG - 1) ? on : kv_last;
+        const double beta = fma(d_i, bo[q], w);
+        const double g = av[q] * beta;
+        const double f = kv ? floor_eps(g) : 0.0;
+        if (q & 1) {
+          dg_b = fma(av[q], bo[q], dg_b);
+          sumF_b += f;
+        } else {
+          dg = fma(av[q], bo[q], dg);
+          sumF += f;
         }
-        for (int tt = 1; tt < len; ++tt) {
-          const double cb = __ldcg(hist + (t0 + tt - 1) * N);
-          const double* orow = obs_j + ph[t0 + tt] * K;
-          double* dst = my_buf + tt * (N * KS);
+        bo[q] = beta * o[q];
+        if (q & 1) rr_b = fma(bo[q], pz[q], rr_b);
+        else rr = fma(bo[q], pz[q], rr);
+        if (on) grow[LPR * q] = g;
+      }
+      sumF += sumF_b;
+      rr += rr_b;
+      dg = (dg + dg_b) * d_i;
+      __syncwarp();       // gamma slice visible to the column owners
+      // column loads first, the row reductions overlap their latency
+      const double* col = gslice + lane;
+      double cs[KC];
 #pragma unroll
-          for (int q = 0; q < KG; ++q) {
-            const double o = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
-            al[q] = o * fma(d_i, al[q], cb * pz[q]);
-            if (on) dst[LPR * q] = al[q];
-          }
+      for (int m = 0; m < KC; ++m) {
+        cs[m] = 0.0;
+        if (lane + 32 * m < K) {
+#pragma unroll
+          for (int ii = 0; ii < N; ++ii) cs[m] += col[ii * KS + 32 * m];
         }
       }
-      for (int tt = len - 1; tt >= 0; --tt) {
-        const int t = t0 + tt;
-        const int x = xb;
-        if (t > 0) xb = ph[t - 1];
-        const bool last = (t == T - 1);
-        // phone-count cells of this step (column owner = lane, fixed), loaded early
-        double tabv[KC];
-        double* trow = tab + x * K + lane;
+      sumF = row_sum_head<LPR>(sumF, j);
+      dg = row_sum_head<LPR>(dg, j);
+      rr = row_sum_head<LPR>(rr, j);
+      if (head) {         // row statistics of this step for the count post-pass
+        __stcg(st + (t * 4 + 1) * N, sumF);
+        __stcg(st + (t * 4 + 2) * N, dg);
+        __stcg(st + (t * 4 + 3) * N, rr);
+      }
+      double wn = 0.0;
 #pragma unroll
-        for (int m = 0; m < KC; ++m) tabv[m] = (lane + 32 * m < K) ? __ldcg(trow + 32 * m) : 0.0;
-        const double* orow = obs_j + x * K;
-        double* row = my_buf + tt * (N * KS);
-        double sumF = 0.0, dg = 0.0, rr = 0.0;
+      for (int jp = 0; jp < N; ++jp) wn = fma(arow[jp], __shfl_sync(0xffffffffu, rr, jp * LPR), wn);
+      w = wn;
+      // conceptCountsA[t][k] = sum_i gamma_t[i][k]; phoneCounts[k][x_t] += ...  (:430,:233,:235)
 #pragma unroll
-        for (int q = 0; q < KG; ++q) {
-          const bool kv = (q < KG - 1) ? on : kv_last;
-          const double av = row[LPR * q];
-          const double beta = last ? 1.0 : fma(d_i, bo[q], w);
-          dg = fma(av, bo[q], dg);
-          const double g = av * beta;
-          sumF += kv ? floor_eps(g) : 0.0;
-          const double o = (q < KG - 1 || kv_last) ? __ldg(orow + LPR * q) : 0.0;
-          bo[q] = beta * o;
-          rr = fma(bo[q], pz[q], rr);
-          if (on) row[LPR * q] = g;
-        }
-        dg *= d_i;
-        __syncwarp();       // gamma slice visible to the column owners
-        // column loads first, the row reductions overlap their latency
-        const double* col = buf + tt * (N * KS) + lane;
-        double cs[KC];
-#pragma unroll
-        for (int m = 0; m < KC; ++m) {
-          cs[m] = 0.0;
-          if (lane + 32 * m < K) {
-#pragma unroll
-            for (int ii = 0; ii < N; ++ii) cs[m] += col[ii * KS + 32 * m];
-          }
-        }
-        sumF = row_sum_head<LPR>(sumF, j);
-        dg = row_sum_head<LPR>(dg, j);
-        rr = row_sum_head<LPR>(rr, j);
-        if (head) {         // row statistics of this step for the count post-pass
-          __stcg(st + (t * 4 + 1) * N, sumF);
-          __stcg(st + (t * 4 + 2) * N, dg);
-          __stcg(st + (t * 4 + 3) * N, rr);
-        }
-        double wn = 0.0;
-#pragma unroll
-        for (int jp = 0; jp < N; ++jp) wn = fma(arow[jp], __shfl_sync(0xffffffffu, rr, jp * LPR), wn);
-        w = wn;
-        // conceptCountsA[t][k] = sum_i gamma_t[i][k]; phoneCounts[k][x_t] += ...  (:430,:233,:235)
-#pragma unroll
-        for (int m = 0; m < KC; ++m) {
-          if (lane + 32 * m < K) {
-            const double v = cs[m] * inorm;
-            __stcg(trow + 32 * m, tabv[m] + v);
-            if (a.cA_out) a.cA_out[(p0 + t) * K + lane + 32 * m] = v;
-          }
+      for (int m = 0; m < KC; ++m) {
+        if (lane + 32 * m < K) {
+          const double v = cs[m] * inorm;
+          __stcg(trow + 32 * m, tabv[m] + v);
+          if (a.cA_out) a.cA_out[(p0 + t) * K + lane + 32 * m] = v;
         }
       }
+    };
+    auto drop_slice = [&](int c) {
       // checkpoint slice c is dead: drop it from L2 instead of letting it be written back
       for (int ln = lane; ln < SL / 16; ln += 32) {
         const double* dead = scr + (size_t)c * SL + ln * 16;
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead) : "memory");
+      }
+    };
+
+    const int nblk = (T + B - 1) / B;
+    if constexpr (RB) {
+      int par = 0;
+      for (int c = nblk - 1; c >= 0; --c) {
+        const int t0 = 2 * c;
+        double a0[KG];
+        {
+          const double* src = my_ckpt + (size_t)c * SL;
+#pragma unroll
+          for (int q = 0; q < KG; ++q) a0[q] = __ldcg(src + 32 * q);
+        }
+        const int x0 = ph[t0];
+        if (t0 + 1 < T) {
+          const int x1 = ph[t0 + 1];
+          const double cb = __ldcg(hist + t0 * N);
+          double o1[KG], a1[KG];
+          load_obs(o1, x1);
+#pragma unroll
+          for (int q = 0; q < KG; ++q) a1[q] = o1[q] * fma(d_i, a0[q], cb * pz[q]);
+          bwd_step(t0 + 1, x1, a1, o1, buf + par * (N * KS));
+          par ^= 1;
+        }
+        {
+          double o0[KG];
+          load_obs(o0, x0);
+          bwd_step(t0, x0, a0, o0, buf + par * (N * KS));
+          par ^= 1;
+        }
+        drop_slice(c);
+      }
+    } else {
+      int xb = ph[T - 1];     // phone of the step about to be processed
+      for (int c = nblk - 1; c >= 0; --c) {
+        const int t0 = c * B;
+        const int len = min(B, T - t0);
+        __syncwarp();         // column reads of the previous block are complete
+        {
+          const double* src = my_ckpt + (size_t)c * SL;
+#pragma unroll
+          for (int q = 0; q < KG; ++q) al[q] = __ldcg(src + 32 * q);
+          if (on) {
+#pragma unroll
+            for (int q = 0; q < KG; ++q) my_buf[LPR * q] = al[q];
+          }
+          for (int tt = 1; tt < len; ++tt) {
+            const double cb = __ldcg(hist + (t0 + tt - 1) * N);
+            double o[KG];
+            load_obs(o, ph[t0 + tt]);
+            double* dst = my_buf + tt * (N * KS);
+#pragma unroll
+            for (int q = 0; q < KG; ++q) {
+              al[q] = o[q] * fma(d_i, al[q], cb * pz[q]);
+              if (on) dst[LPR * q] = al[q];
+            }
+          }
+        }
+        for (int tt = len - 1; tt >= 0; --tt) {
+          const int t = t0 + tt;
+          const int x = xb;
+          if (t > 0) xb = ph[t - 1];
+          double av[KG], o[KG];
+          const double* row = my_buf + tt * (N * KS);
+#pragma unroll
+          for (int q = 0; q < KG; ++q) av[q] = row[LPR * q];
+          load_obs(o, x);
+          bwd_step(t, x, av, o, buf + tt * (N * KS));
+        }
+        drop_slice(c);
       }
     }
   }
@@ -274,7 +344,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
 // host side
 // ------------------------------------------------------------------------------------------
 struct WarpPlan {
-  int KG, B, NC, grid;
+  int KG, B, NC, grid, obs_s, rb;
   size_t smem;
   int64_t warp_scratch;   // doubles per warp
 };
@@ -284,6 +354,8 @@ struct WarpPlan {
 #define MWD_WARP_COMBOS(X)                                                              \
   X(1, 2) X(1, 3) X(1, 4) X(2, 4) X(2, 5) X(2, 7) X(3, 5) X(3, 7) X(3, 10) X(4, 7) X(4, 9) \
   X(4, 13) X(5, 9) X(5, 11) X(6, 10) X(6, 13)
+// register-block variant: compiled for the MSCOCO shape only (experiment knob MWD_ESTEPW_RB=1)
+#define MWD_WARP_RB_COMBOS(X) X(5, 11)
 
 static int warp_kg(int n, int K) {
   const int lpr = 32 / n;
@@ -302,7 +374,7 @@ static bool warp_enabled() {
   return !(e && atoi(e) == 0);
 }
 
-static bool plan_warp(int n, int K, int Tmax, int64_t npairs, WarpPlan* pl) {
+static bool plan_warp(int n, int K, int P, int Tmax, int64_t npairs, WarpPlan* pl) {
   if (n < 1 || n > 6 || !warp_enabled()) return false;
   const int lpr = 32 / n;
   pl->KG = warp_kg(n, K);
@@ -310,7 +382,24 @@ static bool plan_warp(int n, int K, int Tmax, int64_t npairs, WarpPlan* pl) {
   const int ks0 = lpr * pl->KG;
   const int ks = ks0 + (((lpr - ks0) % 16) + 16) % 16;
   const size_t slice = (size_t)kWpc * n * ks * sizeof(double);     // one alpha slice of every warp of a CTA
-  const size_t budget = (size_t)224 * 1024 / kWarpCtasPerSm - 1024;
+  size_t budget = (size_t)224 * 1024 / kWarpCtasPerSm - 1024;
+  // emission table in shared memory when it leaves room for a checkpoint interval of >= 3
+  const size_t obs_bytes = (((size_t)P * K + 1) & ~(size_t)1) * sizeof(double);
+  pl->obs_s = (obs_bytes + 3 * slice <= budget) ? 1 : 0;
+  if (const char* e = getenv("MWD_ESTEPW_OBS")) pl->obs_s = (atoi(e) != 0 && obs_bytes + 2 * slice <= budget) ? 1 : 0;
+  if (pl->obs_s) budget -= obs_bytes;
+  pl->rb = 0;
+  if (const char* e = getenv("MWD_ESTEPW_RB")) {
+    if (atoi(e) != 0) {
+#define X(NN, GG) if (n == NN && pl->KG == GG) pl->rb = 1;
+      MWD_WARP_RB_COMBOS(X)
+#undef X
+    }
+  }
+  if (pl->rb) {   // register block: B = 2, two gamma slices per warp, table in shared memory if it fits
+    pl->obs_s = (obs_bytes + 2 * slice <= (size_t)224 * 1024 / kWarpCtasPerSm - 1024) ? 1 : 0;
+    budget = 2 * slice;
+  }
   int B = (int)(budget / slice);
   if (const char* e = getenv("MWD_ESTEPW_B")) { int v = atoi(e); if (v >= 1 && v < B) B = v; }
   if (B > kWBmax) B = kWBmax;
@@ -319,8 +408,10 @@ static bool plan_warp(int n, int K, int Tmax, int64_t npairs, WarpPlan* pl) {
   pl->B = B;
   pl->NC = (Tmax + B - 1) / B;
   if (pl->NC < 1) pl->NC = 1;
-  pl->smem = (size_t)B * slice;
-  int64_t grid = (int64_t)sm_count() * kWarpCtasPerSm;
+  pl->smem = (size_t)B * slice + (pl->obs_s ? obs_bytes : 0);
+  int ctas_per_sm = kWarpCtasPerSm;
+  if (const char* e = getenv("MWD_ESTEPW_CTAS")) { int v = atoi(e); if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v; }
+  int64_t grid = (int64_t)sm_count() * ctas_per_sm;
   const int64_t need = (npairs + kWpc - 1) / kWpc;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
@@ -330,20 +421,20 @@ static bool plan_warp(int n, int K, int Tmax, int64_t npairs, WarpPlan* pl) {
   return true;
 }
 
-bool estep_warp_supported(int n, int K) {
+bool estep_warp_supported(int n, int K, int P) {
   WarpPlan pl;
-  return plan_warp(n, K, 64, 1 << 20, &pl);
+  return plan_warp(n, K, P, 64, 1 << 20, &pl);
 }
 
-int64_t estep_warp_scratch(int n, int K, int Tmax, int64_t npairs) {
+int64_t estep_warp_scratch(int n, int K, int P, int Tmax, int64_t npairs) {
   WarpPlan pl;
-  if (!plan_warp(n, K, Tmax, npairs, &pl)) return 0;
+  if (!plan_warp(n, K, P, Tmax, npairs, &pl)) return 0;
   return pl.warp_scratch * pl.grid * kWpc;
 }
 
-template <int N, int KG>
+template <int N, int KG, bool OBS_S, bool RB>
 static int launch_warp(const EstepArgs& a, const WarpPlan& pl, cudaStream_t st) {
-  auto kern = ik_estep_warp_kernel<N, KG>;
+  auto kern = ik_estep_warp_kernel<N, KG, OBS_S, RB>;
   MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   kern<<<pl.grid, kWpc * 32, pl.smem, st>>>(a);
   MWD_CHECK_LAUNCH();
@@ -352,11 +443,20 @@ static int launch_warp(const EstepArgs& a, const WarpPlan& pl, cudaStream_t st) 
 
 int estep_warp_launch(EstepArgs a, cudaStream_t st) {
   WarpPlan pl;
-  MWD_REQUIRE(plan_warp(a.n, a.K, a.Tmax, a.hi - a.lo, &pl), "warp E-step: unsupported (n=%d, K=%d)", a.n, a.K);
+  MWD_REQUIRE(plan_warp(a.n, a.K, a.P, a.Tmax, a.hi - a.lo, &pl), "warp E-step: unsupported (n=%d, K=%d)", a.n, a.K);
   a.B = pl.B;
   a.NC = pl.NC;
   a.cta_scratch = pl.warp_scratch;
-#define X(NN, GG) if (a.n == NN && pl.KG == GG) return launch_warp<NN, GG>(a, pl, st);
+  if (pl.rb) {
+#define X(NN, GG)                                                                     \
+  if (a.n == NN && pl.KG == GG)                                                       \
+    return pl.obs_s ? launch_warp<NN, GG, true, true>(a, pl, st) : launch_warp<NN, GG, false, true>(a, pl, st);
+    MWD_WARP_RB_COMBOS(X)
+#undef X
+  }
+#define X(NN, GG)                                                                     \
+  if (a.n == NN && pl.KG == GG)                                                       \
+    return pl.obs_s ? launch_warp<NN, GG, true, false>(a, pl, st) : launch_warp<NN, GG, false, false>(a, pl, st);
   MWD_WARP_COMBOS(X)
 #undef X
   set_error("warp E-step: no instantiation for (n=%d, KG=%d)", a.n, pl.KG);
