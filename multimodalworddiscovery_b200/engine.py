@@ -5,7 +5,6 @@ kernel of libmwd_b200.so called through the C ABI of include/mwd_b200.h.  There 
 fallback: without a CUDA device or without the built library, construction raises.
 """
 import ctypes as C
-import os
 
 import numpy as np
 
@@ -218,26 +217,8 @@ class IKEngine(object):
         self.part.zero_()
         timed('posterior', lambda: self.posterior(width))
         prob = self._problem(with_cA=with_cA and self.cA is not None)
-        if os.environ.get('MWD_OVERLAP', '0') == '1':
-            # experiment: concept chains (FP64-pipe bound) on a side stream next to the recursion
-            # kernel (LSU bound)
-            if not hasattr(self, '_side'):
-                self._side = torch.cuda.Stream(device=self.device)
-            main = torch.cuda.current_stream(self.device)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self._side.wait_event(ev)
-
-            def both():
-                _lib.check(lib.mwd_ik_estep(C.byref(prob), st))
-                _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), C.c_void_p(self._side.cuda_stream)))
-                ev2 = torch.cuda.Event()
-                ev2.record(self._side)
-                main.wait_event(ev2)
-            timed('ik_estep', both)
-        else:
-            timed('ik_estep', lambda: _lib.check(lib.mwd_ik_estep(C.byref(prob), st)))
-            timed('ik_concept', lambda: _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st)))
+        timed('ik_estep', lambda: _lib.check(lib.mwd_ik_estep(C.byref(prob), st)))
+        timed('ik_concept', lambda: _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st)))
         timed('reduce_counts', lambda: _lib.check(lib.mwd_ik_reduce_counts(C.byref(prob), _ptr(self.counts), st)))
         if self.two_layer:
             timed('posterior_grad', self._two_layer_grads)
