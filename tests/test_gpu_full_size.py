@@ -109,12 +109,29 @@ def test_full_size_properties_and_oracle_spot_checks():
         np.testing.assert_allclose(cC[r0:r1].cpu().numpy(), ref['cC'], rtol=1e-9, atol=1e-300)
         np.testing.assert_allclose(eng.pz[r0:r1].cpu().numpy(), ref['pz'], rtol=1e-9, atol=1e-300)
 
-    # sharding invariance: whole corpus == rank 0 of 2 + rank 1 of 2 (fixed order)
+    # sharding invariance: whole corpus == rank 0 of 2 + rank 1 of 2 (fixed order); the halves are
+    # the round-robin deal of the (n, T)-sorted order that corpus.shard_positions prescribes
+    from multimodalworddiscovery_b200.corpus import pack_sorted_arrays, shard_positions
+    from multimodalworddiscovery_b200.engine import IKEngine
     del eng
     torch.cuda.empty_cache()
+    feats = np.asarray(pk.feats).reshape(pk.n_pairs, 5, -1)       # coco5: n == 5 for every pair
     halves = []
     for rank in range(2):
-        _, e2, _ = _run(torch, dev, rank, 2)
+        pos = shard_positions(pk.n_pairs, rank, 2)
+        Th = T[pos]
+        poff = np.concatenate([[0], np.cumsum(Th)]).astype(np.int32)
+        # gather the phones of the selected pairs (vectorised ragged gather)
+        starts = pk.phone_off[pos].astype(np.int64)
+        take = np.repeat(starts - poff[:-1], Th) + np.arange(int(poff[-1]))
+        pkh = pack_sorted_arrays(np.arange(len(pos) + 1, dtype=np.int32) * 5, poff,
+                                 np.ascontiguousarray(feats[pos]).reshape(len(pos) * 5, -1),
+                                 np.ascontiguousarray(np.asarray(pk.phones)[take]), lens=pk.lens,
+                                 n_pairs_global=N_PAIRS)
+        e2 = IKEngine(pkh, K, P, gaussian=False, device=dev, keep_concept_counts_a=False)
+        e2.set_params(params['init'], params['trans'], params['obs'], params['W'])
+        e2.estep(1.0, with_cA=False)
+        torch.cuda.synchronize()
         halves.append(e2.reduced.cpu().numpy().copy())
         del e2
         torch.cuda.empty_cache()
