@@ -31,6 +31,18 @@ constexpr int kWpc = 4;            // warps per CTA
 constexpr int kWarpCtasPerSm = 3;  // 12 warps per SM (register budget 65536 / 384 = 170)
 constexpr int kWBmax = 8;          // max checkpoint interval
 
+// L2 residency hints: the alpha checkpoints are the only global data with reuse (written in the
+// forward sweep, read back once in the backward sweep) -> evict_last; the per-step row statistics
+// are written once for the count post-pass and pz / cA stream through -> evict_first (.cs).
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_keep(double* p, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
 constexpr bool is_pow2(int v) { return (v & (v - 1)) == 0; }
 constexpr int pow2_below(int v) { int p = 1; while (p * 2 < v) p *= 2; return p; }   // largest 2^e < v (v >= 2)
 
@@ -97,6 +109,8 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
   double* tab = a.part_phone + (size_t)gw * a.P * K;
   const double* obs_j = (OBS_S ? smem : a.obsT) + j;             // + x*K + LPR*q
 
+  const uint64_t keep = l2_policy_keep();
+
   auto load_obs = [&](double (&o)[KG], int x) {
     const double* orow = obs_j + x * K;
 #pragma unroll
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
     {
       const double* prow = a.pz + (r0 + i) * K + j;
 #pragma unroll
-      for (int q = 0; q < KG; ++q) pz[q] = (q < KG - 1 ? on : kv_last) ? prow[LPR * q] : 0.0;
+      for (int q = 0; q < KG; ++q) pz[q] = (q < KG - 1 ? on : kv_last) ? __ldcs(prow + LPR * q) : 0.0;
     }
 
     // ------------------------------------------------------------------ forward sweep
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
           if (to_ckpt == 0) {
             double* dst = my_ckpt + (size_t)cidx * SL;
 #pragma unroll
-            for (int q = 0; q < KG; ++q) __stcg(dst + 32 * q, al[q]);
+            for (int q = 0; q < KG; ++q) st_keep(dst + 32 * q, al[q], keep);
             to_ckpt = B;
             ++cidx;
           }
@@ -177,7 +191,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
           for (int jp = 0; jp < N; ++jp) c = fma(acol[jp], sv[jp], c);
           if (head && !a.ll_only) {
             __stcg(hist + t * N, c);
-            __stcg(st + (t * 4 + 0) * N, s);
+            __stcs(st + (t * 4 + 0) * N, s);
           }
 #pragma unroll
           for (int q = 0; q < KG; ++q) al[q] = onext[q] * fma(d_i, al[q], c * pz[q]);
@@ -241,9 +255,9 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
       dg = row_sum_head<LPR>(dg, j);
       rr = row_sum_head<LPR>(rr, j);
       if (head) {         // row statistics of this step for the count post-pass
-        __stcg(st + (t * 4 + 1) * N, sumF);
-        __stcg(st + (t * 4 + 2) * N, dg);
-        __stcg(st + (t * 4 + 3) * N, rr);
+        __stcs(st + (t * 4 + 1) * N, sumF);
+        __stcs(st + (t * 4 + 2) * N, dg);
+        __stcs(st + (t * 4 + 3) * N, rr);
       }
       double wn = 0.0;
 #pragma unroll
