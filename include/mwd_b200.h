@@ -139,6 +139,28 @@ int mwd_outer_grad(const void* feats, int feat_is_f64, int64_t n_regions, int fe
 int mwd_sgd_update(double* param, const double* grad, int64_t elems, double scale, double lr,
                    double momentum, void* stream);
 
+/* ---- dense-emission classes: ImageAudioHMMWordDiscoverer -------------------------
+ * hmm_dnn/image_audio_hmm_word_discoverer.py replaces the discrete emission obs[:, x_t] by
+ *     E[t][k] = sum_ph phoneProbs[k][ph] * p(ph | a_t)          (:286-288, :320-322, :384-386)
+ * with p(ph | a_t) = softmaxLayerA(a_t) (:549-554) = mwd_posterior_linear over the audio frames.
+ * The recursion / concept / decode entry points run unchanged on
+ *     obsT = emis (n_frames x K),  phones[f] = f (identity),  n_phone_types = n_frames,
+ *     part_phone = NULL (no phone table: mwd_ik_estep then only fills concept_counts_a and
+ *     mwd_ik_reduce_counts zeroes the phone block of `counts`).
+ * mwd_dense_emission:      emis[f][k] from frame_post (n_frames x n_phones) and phone_probs_t
+ *                          (n_phones x K, the obsT layout of phoneProbs).
+ * mwd_concept_phone_counts: updateConceptPhoneCounts (:486-493) summed over the frames, i.e. the
+ *                          phoneCounts of trainUsingEM :230-231 in the obsT layout:
+ *     counts_t[ph][k] = sum_f cA[f][k] * frame_post[f][ph] / (sum_k cA[f] * sum_ph frame_post[f])
+ *                          partials [dev]: mwd_concept_phone_partials_len() doubles of scratch;
+ *                          frames are summed in order inside fixed chunks, chunks in order.        */
+int mwd_dense_emission(const double* frame_post, const double* phone_probs_t, int64_t n_frames,
+                       int n_phones, int n_concepts, double* emis, void* stream);
+int64_t mwd_concept_phone_partials_len(int n_concepts, int n_phones);
+int mwd_concept_phone_counts(const double* concept_counts_a, const double* frame_post, int64_t n_frames,
+                             int n_concepts, int n_phones, double* partials, double* counts_t,
+                             void* stream);
+
 /* forward + backward + updateInitialCounts + updateTransitionCounts + updateStateCounts +
  * computeAvgLogLikelihood -- image_phone_hmm_word_discoverer.py:276-433, 523-531, and the
  * phoneCounts / conceptCountsA accumulation of trainUsingEM :230-235.

@@ -94,6 +94,9 @@ SYMBOLS = {
     'mwd_backprop_hidden': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
     'mwd_outer_grad': (_i, [_vp, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     'mwd_sgd_update': (_i, [_vp, _vp, _i64, _d, _d, _d, _vp]),
+    'mwd_dense_emission': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    'mwd_concept_phone_partials_len': (_i64, [_i, _i]),
+    'mwd_concept_phone_counts': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     'mwd_ik_estep': (_i, [C.POINTER(IkProblem), _vp]),
     'mwd_ik_loglik': (_i, [C.POINTER(IkProblem), _vp]),
     'mwd_ik_partial_sizes': (_i, [_i, _i, C.POINTER(PartialSizes)]),

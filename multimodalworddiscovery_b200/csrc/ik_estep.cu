@@ -111,6 +111,8 @@ ik_estep_kernel(const EstepArgs a) {
   double* my_hist = cta_scr + (size_t)PP * a.NC * SL + (size_t)slot * a.Tmax * n + i;  // + t*n : c_t[i]
   const int buf_row = (slot * B * n + i) * KS + l8;                                  // + tt*n*KS + 8j
   const int nKS = n * KS;
+  // part_phone == NULL (dense-emission classes): no phone table, the caller consumes cA_out instead
+  const bool tab_on = a.part_phone != nullptr;
   double* g_phone = a.part_phone + (size_t)blockIdx.x * a.P * K;
   double* tab = TAB ? (smem + o_tab) : g_phone;
   const int* my_x = s_x + slot * TX;
@@ -312,8 +314,9 @@ ik_estep_kernel(const EstepArgs a) {
         // drain the phone-count rows deferred by the previous step: thread k owns column k of
         // the per-CTA table for every slot, so the read-modify-writes never race and their
         // order (t descending, slot ascending) is fixed.
-        for (int k = tid; k < K; k += blockDim.x)
-          drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
+        if (tab_on)
+          for (int k = tid; k < K; k += blockDim.x)
+            drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
         if (i == 0 && l8 == 0) s_xs[par][slot] = act ? x : -1;
         if (act) {
           const double* ex = s_exch + exo;
@@ -345,15 +348,16 @@ ik_estep_kernel(const EstepArgs a) {
     {
       const int par = step & 1;
       __syncthreads();
-      for (int k = tid; k < K; k += blockDim.x)
-        drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
+      if (tab_on)
+        for (int k = tid; k < K; k += blockDim.x)
+          drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
     }
   }
 
   if (a.ll_only) return;
   // ---------------------------------------------------------------- per-CTA phone-count table
   __syncthreads();
-  if (TAB)
+  if (TAB && tab_on)
     for (int e = tid; e < a.P * K; e += blockDim.x) g_phone[e] += smem[o_tab + e];
 }
 

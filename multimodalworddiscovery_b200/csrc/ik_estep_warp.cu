@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
   double* scr = a.scratch + (size_t)gw * a.cta_scratch;          // [NC][SL] checkpoints, [Tmax][N] c_t
   double* my_ckpt = scr + lane;                                  // + c*SL + 32*q
   double* hist = scr + (size_t)a.NC * SL + i;                    // + t*N
+  // part_phone == NULL (dense-emission classes): no phone table, the caller consumes cA_out instead
+  const bool tab_on = a.part_phone != nullptr;
   double* tab = a.part_phone + (size_t)gw * a.P * K;
   const double* obs_j = (OBS_S ? smem : a.obsT) + j;             // + x*K + LPR*q
 
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
       double tabv[KC];
       double* trow = tab + x * K + lane;
 #pragma unroll
-      for (int m = 0; m < KC; ++m) tabv[m] = (lane + 32 * m < K) ? __ldcg(trow + 32 * m) : 0.0;
+      for (int m = 0; m < KC; ++m) tabv[m] = (tab_on && lane + 32 * m < K) ? __ldcg(trow + 32 * m) : 0.0;
       double* grow = gslice + i * KS + j;
       double sumF = 0.0, dg = 0.0, rr = 0.0, sumF_b = 0.0, dg_b = 0.0, rr_b = 0.0;   // two chains each
 #pragma unroll
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
 #pragma unroll
       for (int m = 0; m < KC; ++m) {
         cs[m] *= inorm;
-        if (lane + 32 * m < K) __stcg(trow + 32 * m, tabv[m] + cs[m]);
+        if (tab_on && lane + 32 * m < K) __stcg(trow + 32 * m, tabv[m] + cs[m]);
       }
       if (a.cA_out) {
         double* crow = a.cA_out + (p0 + t) * K + lane;

@@ -160,7 +160,10 @@ extern "C" int mwd_ik_reduce_counts(const mwd_ik_problem* p, double* counts, voi
   const int64_t pe = (int64_t)p->n_phone_types * p->n_concepts;
   const int64_t ie = (int64_t)(kNMax + 1) * kNMax;
   const int64_t te = (int64_t)(kNMax + 1) * kNMax * kNMax;
-  reduce_rows_kernel<<<(unsigned)((pe + 255) / 256), 256, 0, st>>>(p->part_phone, rows, pe, counts);
+  if (p->part_phone)
+    reduce_rows_kernel<<<(unsigned)((pe + 255) / 256), 256, 0, st>>>(p->part_phone, rows, pe, counts);
+  else   // dense-emission classes fill counts[0:pe] themselves (mwd_concept_phone_counts)
+    MWD_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)pe * sizeof(double), st));
   reduce_rows_kernel<<<(unsigned)((ie + 255) / 256), 256, 0, st>>>(p->part_init, rows, ie, counts + pe);
   reduce_rows_kernel<<<(unsigned)((te + 255) / 256), 256, 0, st>>>(p->part_trans, rows, te,
                                                                    counts + pe + ie);

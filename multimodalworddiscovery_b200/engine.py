@@ -405,9 +405,11 @@ class IKEngine(object):
             return ali[:pk.n_phones_total], ic[:pk.n_regions], ap, cs[:pk.n_regions]
         return ali[:pk.n_phones_total], ic[:pk.n_regions], ap
 
-    def decode_pair(self, v, x, floor_norm=False, width=1.0, alignment=None):
+    def decode_pair(self, v, x, floor_norm=False, width=1.0, alignment=None, obsT=None):
         """align()/cluster() of ONE arbitrary pair under the current parameters.
-        Returns (alignment (T,), align_probs (T, n), image_concepts (n,), cluster_scores (n, K))."""
+        Returns (alignment (T,), align_probs (T, n), image_concepts (n,), cluster_scores (n, K)).
+        ``obsT``: optional device emission table (rows x K) used instead of the model's (the
+        dense-emission classes pass the pair's E and x = arange(T))."""
         torch = self.torch
         dev = self.device
         n, T = int(v.shape[0]), int(len(x))
@@ -427,6 +429,8 @@ class IKEngine(object):
         p.t_max, p.n_buckets = T, 0
         p.region_off, p.phone_off, p.feats, p.phones = _ptr(roff), _ptr(poff), _ptr(v_d), _ptr(x_d)
         p.init, p.trans, p.obsT, p.pz = _ptr(self.init_t), _ptr(self.trans_t), _ptr(self.obsT), _ptr(pz)
+        if obsT is not None:
+            p.obsT, p.n_phone_types = _ptr(obsT), int(obsT.shape[0])
         given = alignment is not None
         if given:
             ali = torch.from_numpy(np.ascontiguousarray(alignment, dtype=np.int32)).to(dev)
@@ -450,9 +454,10 @@ class IKEngine(object):
         _lib.check(self.lib.mwd_argmax_rows(_ptr(self.cA), Tt, self.K, _ptr(out), self._stream()))
         return out[:Tt]
 
-    def dense_sweep(self, pz_pair, phones_pair, backward=False):
+    def dense_sweep(self, pz_pair, phones_pair, backward=False, obsT=None):
         """forward()/backward() of one pair: (T, n, K) tensor under the current parameters."""
         torch = self.torch
+        obsT = self.obsT if obsT is None else obsT
         pz_d = torch.from_numpy(np.ascontiguousarray(pz_pair, dtype=np.float64)).to(self.device)
         ph_d = torch.from_numpy(np.ascontiguousarray(phones_pair, dtype=np.int32)).to(self.device)
         n, K = pz_pair.shape
@@ -460,10 +465,10 @@ class IKEngine(object):
         out = torch.zeros((T, n, K), dtype=torch.float64, device=self.device)
         if backward:
             _lib.check(self.lib.mwd_ik_backward_dense(_ptr(pz_d), _ptr(ph_d), T, n, K, _ptr(self.trans_t),
-                                                      _ptr(self.obsT), _ptr(out), self._stream()))
+                                                      _ptr(obsT), _ptr(out), self._stream()))
         else:
             _lib.check(self.lib.mwd_ik_forward_dense(_ptr(pz_d), _ptr(ph_d), T, n, K, _ptr(self.init_t),
-                                                     _ptr(self.trans_t), _ptr(self.obsT), _ptr(out),
+                                                     _ptr(self.trans_t), _ptr(obsT), _ptr(out),
                                                      self._stream()))
         return out.cpu().numpy()
 

@@ -1,0 +1,123 @@
+"""Device engine of the dense-emission class ``ImageAudioHMMWordDiscoverer`` (SURVEY 8 f2,
+reference hmm_dnn/image_audio_hmm_word_discoverer.py).
+
+The model is the image-phone (region i, concept k)-state HMM whose discrete emission ``obs[:, x_t]``
+is replaced by ``E[t] = phoneProbs @ softmaxLayerA(a_t)`` (:286-288).  The recursion, concept-chain
+and Viterbi kernels therefore run unchanged on ``obsT = E`` (frames x K) with the identity phone
+sequence; this engine adds the frame posterior / dense emission GEMMs in front and the
+concept-phone count reduction (updateConceptPhoneCounts :486-493, phoneCounts :230-231) behind.
+No CPU fallback, like ``IKEngine``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .corpus import pack_pairs
+from .engine import IKEngine, _ptr
+
+
+def pack_audio_pairs(feats_list, audio_list, feat_dtype=np.float32, rank=0, world=1):
+    """Sort by (n regions, T frames) and shard like ``pack_pairs``; returns (packed, audio) where
+    ``audio`` is the (frames, Da) float64 matrix in packed order and ``packed.phones`` is the identity
+    frame index (the kernels read emission row ``phones[t]``)."""
+    pk = pack_pairs(feats_list, [np.zeros(len(a), dtype=np.int32) for a in audio_list], feat_dtype=feat_dtype,
+                    rank=rank, world=world)
+    Da = audio_list[0].shape[1] if len(audio_list) else 0
+    rows = [np.asarray(audio_list[int(ex)], dtype=np.float64).reshape(-1, Da) for ex in pk.order]
+    audio = np.concatenate(rows, axis=0) if rows else np.zeros((0, Da))
+    pk.phones = np.arange(pk.n_phones_total, dtype=np.int32)
+    return pk, np.ascontiguousarray(audio)
+
+
+class IKAudioEngine(IKEngine):
+    def __init__(self, packed, audio, n_concepts, n_phones, device=None, process_group=None):
+        self._audio_ready = False
+        self.nPh = int(n_phones)
+        if packed.n_phones_total * int(n_concepts) >= 2 ** 31:
+            raise ValueError('dense emission table of %d frames x %d concepts exceeds 2^31 entries per shard'
+                             % (packed.n_phones_total, n_concepts))
+        IKEngine.__init__(self, packed, n_concepts, n_phones, gaussian=False, device=device,
+                          keep_concept_counts_a=True, process_group=process_group)
+        torch, dev, f64 = self.torch, self.device, self.torch.float64
+        Tt = max(packed.n_phones_total, 1)
+        self.Da = int(audio.shape[1])
+        self.afeats = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float64)).to(dev)
+        self.WA = torch.zeros((self.nPh, self.Da + 1), dtype=f64, device=dev)
+        self.gradA0 = torch.zeros((self.nPh, self.Da + 1), dtype=f64, device=dev)
+        self.PH = torch.empty((Tt, self.nPh), dtype=f64, device=dev)
+        self.E = torch.empty((Tt, self.K), dtype=f64, device=dev)
+        self.cpc_partials = torch.empty((int(self.lib.mwd_concept_phone_partials_len(self.K, self.nPh)),),
+                                        dtype=f64, device=dev)
+        self._audio_ready = True
+
+    # the kernels see the dense emission table as a (frames x K) obsT and no phone-count table
+    def _problem(self, with_cA=True):
+        p = IKEngine._problem(self, with_cA=with_cA)
+        p.n_phone_types = max(self.pk.n_phones_total, 1)
+        p.part_phone = C.c_void_p(0)
+        if self._audio_ready:
+            p.obsT = _ptr(self.E)
+        return p
+
+    def set_audio_param(self, WA):
+        WA = np.ascontiguousarray(np.asarray(WA, dtype=np.float64))
+        if WA.shape != tuple(self.WA.shape):
+            raise ValueError('WA shape %s != %s' % (WA.shape, tuple(self.WA.shape)))
+        self.WA.copy_(self.torch.from_numpy(WA))
+
+    def get_audio_param(self):
+        return self.WA.cpu().numpy().copy()
+
+    def posterior(self, width=1.0):
+        """pz (softmaxLayerV :543-547), frame posteriors (softmaxLayerA :549-554) and E (:288)."""
+        IKEngine.posterior(self, width)
+        lib, st = self.lib, self._stream()
+        Tt = self.pk.n_phones_total
+        _lib.check(lib.mwd_posterior_linear(_ptr(self.afeats), 1, Tt, self.Da, _ptr(self.WA), self.nPh,
+                                            _ptr(self.PH), st))
+        _lib.check(lib.mwd_dense_emission(_ptr(self.PH), _ptr(self.obsT), Tt, self.nPh, self.K, _ptr(self.E), st))
+
+    def estep(self, width=1.0, with_cA=True, timers=None):
+        lib, st = self.lib, self._stream()
+        self.part.zero_()
+        self.posterior(width)
+        prob = self._problem(with_cA=True)
+        _lib.check(lib.mwd_ik_estep(C.byref(prob), st))
+        _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st))
+        red = self._problem(with_cA=True)
+        red.n_phone_types = self.nPh                  # layout of `counts`: phone block is nPhones x K
+        _lib.check(lib.mwd_ik_reduce_counts(C.byref(red), _ptr(self.counts), st))
+        _lib.check(lib.mwd_concept_phone_counts(_ptr(self.cA), _ptr(self.PH), self.pk.n_phones_total, self.K,
+                                                self.nPh, _ptr(self.cpc_partials), _ptr(self.counts), st))
+        _lib.check(lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st))
+
+    def mstep(self, lr, momentum, width=1.0, freeze_trans=False):
+        IKEngine.mstep(self, lr, momentum, width, freeze_trans)
+        # updateSoftmaxWeightA (:527-541): Delta = sum_k conceptPhoneCount - phProb vanishes identically
+        # (the per-frame normalised outer product summed over k IS phProb), the reference's dW is
+        # rounding noise <= 1e-17 (tests/golden/ia_*.npz) -> WA <- (1 - momentum) * WA
+        _lib.check(self.lib.mwd_sgd_update(_ptr(self.WA), _ptr(self.gradA0), self.WA.numel(), 1.0, float(lr),
+                                           float(momentum), self._stream()))
+
+    # ------------------------------------------------------------------ single-pair API
+    def emission_rows(self, a):
+        """(softmaxLayerA(aSen), probs_x_given_z) of an arbitrary (T, Da) frame block: device tensors."""
+        torch = self.torch
+        a_d = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        T = int(a_d.shape[0])
+        ph = torch.empty((max(T, 1), self.nPh), dtype=torch.float64, device=self.device)
+        E = torch.empty((max(T, 1), self.K), dtype=torch.float64, device=self.device)
+        st = self._stream()
+        _lib.check(self.lib.mwd_posterior_linear(_ptr(a_d), 1, T, self.Da, _ptr(self.WA), self.nPh, _ptr(ph), st))
+        _lib.check(self.lib.mwd_dense_emission(_ptr(ph), _ptr(self.obsT), T, self.nPh, self.K, _ptr(E), st))
+        return ph[:T], E[:T]
+
+    def decode_pair_audio(self, v, a, alignment=None):
+        _, E = self.emission_rows(a)
+        return self.decode_pair(v, np.arange(len(a), dtype=np.int32), floor_norm=True, alignment=alignment, obsT=E)
+
+    def dense_sweep_audio(self, v, a, backward=False):
+        _, E = self.emission_rows(a)
+        pz = self.posterior_rows(np.asarray(v))
+        return self.dense_sweep(pz, np.arange(len(a), dtype=np.int32), backward=backward, obsT=E)

@@ -20,16 +20,17 @@ sys.path.insert(0, %r)                      # the driver's own directory comes f
 from hmm_dnn.image_phone_hmm_word_discoverer import *
 from hmm_dnn.image_phone_hmm_dnn_word_discoverer import *      # run_image2phone.py:2
 from hmm_dnn.image_phone_gaussian_hmm_word_discoverer import *
-from hmm_dnn.image_audio_hmm_word_discoverer import *          # run_image2audio.py -- reference file
+from hmm_dnn.image_audio_hmm_word_discoverer import *          # run_image2audio.py:9
+from hmm_dnn.image_audio_gaussian_hmm_word_discoverer import * # run_image2audio.py -- reference file (not mirrored)
 from hmm.hmm_word_discoverer import *
 from hmm.audio_segembed_hmm_word_discoverer import *
 from hmm.audio_hmm_word_discoverer import *
 from utils.clusteval import *               # reference module; needs the nltk / matplotlib stubs
 from utils.postprocess import *
 for cls in (ImagePhoneHMMWordDiscoverer, ImagePhoneGaussianHMMWordDiscoverer, HMMWordDiscoverer, AudioHMMWordDiscoverer,
-            SegEmbedHMMWordDiscoverer, ImagePhoneHMMDNNWordDiscoverer):
+            SegEmbedHMMWordDiscoverer, ImagePhoneHMMDNNWordDiscoverer, ImageAudioHMMWordDiscoverer):
     assert cls.__module__.startswith('multimodalworddiscovery_b200.'), cls.__module__
-assert ImageAudioHMMWordDiscoverer.__module__ == 'hmm_dnn.image_audio_hmm_word_discoverer'
+assert ImageAudioGaussianHMMWordDiscoverer.__module__ == 'hmm_dnn.image_audio_gaussian_hmm_word_discoverer'
 assert np.__name__ == 'numpy' and json.__name__ == 'json'   # names the drivers rely on (run_image2phone.py:132,137)
 print('OK')
 ''' % REF
