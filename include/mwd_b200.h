@@ -186,7 +186,8 @@ int mwd_ik_concept_counts(const mwd_ik_problem* p, void* stream);
 /* Deterministic second-level reduction of the per-CTA partials (fixed order, no atomics):
  *   counts = [ phoneC (P x K, transposed) | initC ((NMAX+1) x NMAX) | transC ((NMAX+1) x NMAX^2) | sum LL ]
  * `counts` [dev] has mwd_ik_counts_len(K,P) doubles; this is the buffer that is all-reduced
- * across GPUs before the M-step.                                                            */
+ * across GPUs before the M-step.  The partial tables are CONSUMED (the first reduction level
+ * parks its sums in place): zero them before the next E-step, call this once per iteration.   */
 int64_t mwd_ik_counts_len(int n_concepts, int n_phone_types);
 int mwd_ik_reduce_counts(const mwd_ik_problem* p, double* counts, void* stream);
 
