@@ -131,7 +131,9 @@ int mwd_backprop_hidden(const double* concept_counts, const double* pz, const do
 /* grad[m][d] = sum_r (delta - minus)[r][m] * [feats[r], 1][d]   (n_rows_out x (D+1), UNscaled);
  * `minus` may be NULL.  The two weight gradients of :522-526 are two calls of this
  * (delta = concept_counts, minus = pz over the hidden activations; delta = eps over the features).
- * grad_partials [dev]: grad_splits x min(n_rows_out,128) x (D+1) scratch.                      */
+ * grad_partials [dev]: mwd_outer_grad_partials_len(n_rows_out, D) doubles of scratch (row splits
+ * x min(n_rows_out,128) x (D+1); narrow feature matrices get more row splits).                 */
+int64_t mwd_outer_grad_partials_len(int n_rows_out, int feat_dim);
 int mwd_outer_grad(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
                    const double* delta, const double* minus, int n_rows_out, double* grad_partials,
                    double* grad, void* stream);
@@ -148,16 +150,18 @@ int mwd_sgd_update(double* param, const double* grad, int64_t elems, double scal
  *     part_phone = NULL (no phone table: mwd_ik_estep then only fills concept_counts_a and
  *     mwd_ik_reduce_counts zeroes the phone block of `counts`).
  * mwd_dense_emission:      emis[f][k] from frame_post (n_frames x n_phones) and phone_probs_t
- *                          (n_phones x K, the obsT layout of phoneProbs).
+ *                          (n_phones x K, the obsT layout of phoneProbs); a GEMM on the FP64 tensor
+ *                          path.  v_scratch [dev]: K x (n_phones+1) doubles.
  * mwd_concept_phone_counts: updateConceptPhoneCounts (:486-493) summed over the frames, i.e. the
  *                          phoneCounts of trainUsingEM :230-231 in the obsT layout:
  *     counts_t[ph][k] = sum_f cA[f][k] * frame_post[f][ph] / (sum_k cA[f] * sum_ph frame_post[f])
- *                          partials [dev]: mwd_concept_phone_partials_len() doubles of scratch;
- *                          frames are summed in order inside fixed chunks, chunks in order.        */
+ *                          concept_counts_a is NORMALISED IN PLACE (rows divided by the bracket), then
+ *                          reduced by the outer-product GEMM with deterministic row-split partials.
+ *                          partials [dev]: mwd_concept_phone_partials_len() doubles of scratch.      */
 int mwd_dense_emission(const double* frame_post, const double* phone_probs_t, int64_t n_frames,
-                       int n_phones, int n_concepts, double* emis, void* stream);
+                       int n_phones, int n_concepts, double* v_scratch, double* emis, void* stream);
 int64_t mwd_concept_phone_partials_len(int n_concepts, int n_phones);
-int mwd_concept_phone_counts(const double* concept_counts_a, const double* frame_post, int64_t n_frames,
+int mwd_concept_phone_counts(double* concept_counts_a, const double* frame_post, int64_t n_frames,
                              int n_concepts, int n_phones, double* partials, double* counts_t,
                              void* stream);
 
@@ -194,7 +198,7 @@ int mwd_ik_reduce_counts(const mwd_ik_problem* p, double* counts, void* stream);
 /* Gradient of the image-posterior parameters -- updateSoftmaxWeight,
  * image_phone_hmm_word_discoverer.py:475-488 (linear) / gaussian :488-499:
  *   grad[k][d] = sum_r (concept_counts - pz)[r][k] * [feats[r], 1][d]     (K x (D+1), UNscaled)
- * grad_partials [dev] : grad_splits x K x (D+1);  grad [dev] : K x (D+1).                    */
+ * grad_partials [dev] : mwd_outer_grad_partials_len(K, D) doubles;  grad [dev] : K x (D+1).    */
 int mwd_ik_posterior_grad(const mwd_ik_problem* p, double* grad_partials, double* grad,
                           void* stream);
 /* Streaming form for corpora processed in chunks (host-resident or larger than HBM): add one

@@ -92,9 +92,10 @@ SYMBOLS = {
     'mwd_posterior_gaussian': (_i, [_vp, _i, _i64, _i, _vp, _d, _i, _vp, _vp, _vp]),
     'mwd_hidden_relu': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp, _vp]),
     'mwd_backprop_hidden': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
+    'mwd_outer_grad_partials_len': (_i64, [_i, _i]),
     'mwd_outer_grad': (_i, [_vp, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     'mwd_sgd_update': (_i, [_vp, _vp, _i64, _d, _d, _d, _vp]),
-    'mwd_dense_emission': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    'mwd_dense_emission': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     'mwd_concept_phone_partials_len': (_i64, [_i, _i]),
     'mwd_concept_phone_counts': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     'mwd_ik_estep': (_i, [C.POINTER(IkProblem), _vp]),

@@ -362,14 +362,24 @@ struct GradIn {
   const double* delta; const double* minus; int ldc; int K;
 };
 
+// Row splits of the gradient GEMM: kGradSplits x 4 d-tiles fill the machine at D = 512; narrower
+// feature matrices (fewer d-tiles) get proportionally more row splits so the grid stays ~296 CTAs.
+static int grad_splits_for(int D) {
+  const int dt = (D + BD - 1) / BD;
+  int m = 4 / (dt < 1 ? 1 : dt);
+  if (m < 1) m = 1;
+  return kGradSplits * m;
+}
+
 template <int MT8>
 static int launch_grad(const GradIn& g, double* partial, int accumulate, cudaStream_t st) {
   const int D = g.D, K = g.K;
   const int64_t R = g.R;
-  int64_t rps = (R + kGradSplits - 1) / kGradSplits;
+  const int splits = grad_splits_for(D);
+  int64_t rps = (R + splits - 1) / splits;
   rps = ((rps + BR - 1) / BR) * BR;
   if (rps < BR) rps = BR;
-  dim3 grid((D + BD - 1) / BD, kGradSplits);
+  dim3 grid((D + BD - 1) / BD, splits);
   if (g.feat_is_f64)
     posterior_grad_kernel<MT8, double><<<grid, 256, 0, st>>>((const double*)g.feats, R, D, g.delta, g.minus,
                                                              g.ldc, K, rps, partial, accumulate);
@@ -460,6 +470,11 @@ extern "C" int mwd_backprop_hidden(const double* concept_counts, const double* p
   return 0;
 }
 
+extern "C" int64_t mwd_outer_grad_partials_len(int n_rows_out, int feat_dim) {
+  const int rows = n_rows_out < MWD_KMAX ? n_rows_out : MWD_KMAX;
+  return (int64_t)grad_splits_for(feat_dim) * rows * (feat_dim + 1);
+}
+
 extern "C" int mwd_outer_grad(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
                               const double* delta, const double* minus, int n_rows_out, double* grad_partials,
                               double* grad, void* stream) {
@@ -471,8 +486,8 @@ extern "C" int mwd_outer_grad(const void* feats, int feat_is_f64, int64_t n_regi
     int rc = grad_generic(g, grad_partials, 0, st);
     if (rc) return rc;
     const int64_t elems = (int64_t)rows * ld;
-    grad_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(grad_partials, kGradSplits, elems,
-                                                                        grad + (size_t)c0 * ld);
+    grad_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(grad_partials, grad_splits_for(feat_dim),
+                                                                        elems, grad + (size_t)c0 * ld);
     MWD_CHECK_LAUNCH();
   }
   return 0;
@@ -514,7 +529,7 @@ extern "C" int mwd_ik_posterior_grad_finish(int n_concepts, int feat_dim, const 
                                             double* grad, void* stream) {
   const int64_t elems = (int64_t)n_concepts * (feat_dim + 1);
   grad_reduce_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, as_stream(stream)>>>(
-      grad_partials, kGradSplits, elems, grad);
+      grad_partials, grad_splits_for(feat_dim), elems, grad);
   MWD_CHECK_LAUNCH();
   return 0;
 }

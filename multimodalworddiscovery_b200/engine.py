@@ -97,9 +97,11 @@ class IKEngine(object):
         self.counts = self.reduced[:self.counts_len]
         self.grad = self.reduced[self.counts_len:self.counts_len + self.grad_len]
         self.gradV = self.reduced[self.counts_len + self.grad_len:]
-        gp_rows = max(self.K, min(self.H, _lib.KMAX))
-        gp_cols = max(self.D, self.H) + 1
-        self.grad_partials = torch.empty((self.geom.grad_splits, gp_rows, gp_cols), dtype=f64, device=dev)
+        gp_len = int(self.lib.mwd_outer_grad_partials_len(self.K, self.D))
+        if self.two_layer:
+            gp_len = max(gp_len, int(self.lib.mwd_outer_grad_partials_len(self.K, self.H)),
+                         int(self.lib.mwd_outer_grad_partials_len(self.H, self.D)))
+        self.grad_partials = torch.empty((gp_len,), dtype=f64, device=dev)
         self._lens = np.ascontiguousarray(np.array(packed.lens, dtype=np.int32))
         self.toeplitz = 1 if len(packed.lens) >= 6 else 0     # :399
         self.n_pairs_global = int(packed.n_pairs_global)

@@ -47,6 +47,7 @@ class IKAudioEngine(IKEngine):
         self.gradA0 = torch.zeros((self.nPh, self.Da + 1), dtype=f64, device=dev)
         self.PH = torch.empty((Tt, self.nPh), dtype=f64, device=dev)
         self.E = torch.empty((Tt, self.K), dtype=f64, device=dev)
+        self.v_scratch = torch.empty((self.K, self.nPh + 1), dtype=f64, device=dev)
         self.cpc_partials = torch.empty((int(self.lib.mwd_concept_phone_partials_len(self.K, self.nPh)),),
                                         dtype=f64, device=dev)
         self._audio_ready = True
@@ -76,7 +77,8 @@ class IKAudioEngine(IKEngine):
         Tt = self.pk.n_phones_total
         _lib.check(lib.mwd_posterior_linear(_ptr(self.afeats), 1, Tt, self.Da, _ptr(self.WA), self.nPh,
                                             _ptr(self.PH), st))
-        _lib.check(lib.mwd_dense_emission(_ptr(self.PH), _ptr(self.obsT), Tt, self.nPh, self.K, _ptr(self.E), st))
+        _lib.check(lib.mwd_dense_emission(_ptr(self.PH), _ptr(self.obsT), Tt, self.nPh, self.K,
+                                          _ptr(self.v_scratch), _ptr(self.E), st))
 
     def estep(self, width=1.0, with_cA=True, timers=None):
         lib, st = self.lib, self._stream()
@@ -110,7 +112,8 @@ class IKAudioEngine(IKEngine):
         E = torch.empty((max(T, 1), self.K), dtype=torch.float64, device=self.device)
         st = self._stream()
         _lib.check(self.lib.mwd_posterior_linear(_ptr(a_d), 1, T, self.Da, _ptr(self.WA), self.nPh, _ptr(ph), st))
-        _lib.check(self.lib.mwd_dense_emission(_ptr(ph), _ptr(self.obsT), T, self.nPh, self.K, _ptr(E), st))
+        _lib.check(self.lib.mwd_dense_emission(_ptr(ph), _ptr(self.obsT), T, self.nPh, self.K,
+                                               _ptr(self.v_scratch), _ptr(E), st))
         return ph[:T], E[:T]
 
     def decode_pair_audio(self, v, a, alignment=None):
