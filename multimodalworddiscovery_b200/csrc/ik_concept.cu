@@ -12,6 +12,8 @@
 // lives in __constant__ memory so every DFMA takes it as an immediate constant-bank operand, the
 // marginal emissions are broadcast from shared memory, obs[.][x_t] comes from the transposed
 // (P x K) table through L1.  Raw float64 probability domain, no floors -- as the reference.
+#include <type_traits>
+
 #include "mwd_common.cuh"
 
 namespace mwd {
@@ -63,43 +65,78 @@ __global__ void __launch_bounds__(1024) ik_concept_kernel(const ConceptArgs a) {
 
   const double* A = c_trans + N * (kNMax * kNMax);
   const double* pi = c_init + N * kNMax;
-  // one step of the restricted chain: G = (F A) * e', e'[j] = e_t[j] except e'[i] = o
-  auto chain_step = [&](const double (&F)[N], double (&G)[N], const double* et, double o, int i) {
+  // one step of the restricted chain: G = (F A) * e', e'[j] = e_t[j] except e'[i] = o.
+  // SI >= 0: the clamped region is a compile-time constant (warp-uniform chains), so the emission
+  // pick costs nothing; SI < 0: generic per-thread select.
+  auto chain_step = [&](auto si_tag, const double (&F)[N], double (&G)[N], const double* et, double o, int i) {
+    constexpr int SI = decltype(si_tag)::value;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       double acc = 0.0;
 #pragma unroll
       for (int l = 0; l < N; ++l) acc = fma(F[l], A[l * N + j], acc);
-      G[j] = acc * ((j == i) ? o : et[j]);
+      if (SI >= 0) G[j] = acc * ((j == SI) ? o : et[j]);
+      else G[j] = acc * ((j == i) ? o : et[j]);
     }
   };
-  for (int c = tid; c < N * K; c += blockDim.x) {
-    const int i = c / K, k = c - i * K;
+  // whole restricted chain of (region i, concept k); returns pz[i][k] * L(i,k)
+  auto run_chain = [&](auto si_tag, int i, int k) {
+    constexpr int SI = decltype(si_tag)::value;
     const double* ocol = a.obsT + k;
     double F[N], G[N];
     {
       double o = __ldg(ocol + (size_t)s_x[0] * K);
 #pragma unroll
-      for (int j = 0; j < N; ++j) F[j] = pi[j] * ((j == i) ? o : s_e[j]);
+      for (int j = 0; j < N; ++j) F[j] = pi[j] * ((j == (SI >= 0 ? SI : i)) ? o : s_e[j]);
     }
     int t = 1;
     // two steps per trip (F -> G -> F): no register copies between steps
     for (; t + 1 < T; t += 2) {
       const double o0 = __ldg(ocol + (size_t)s_x[t] * K);
       const double o1 = __ldg(ocol + (size_t)s_x[t + 1] * K);
-      chain_step(F, G, s_e + t * N, o0, i);
-      chain_step(G, F, s_e + (t + 1) * N, o1, i);
+      chain_step(si_tag, F, G, s_e + t * N, o0, i);
+      chain_step(si_tag, G, F, s_e + (t + 1) * N, o1, i);
     }
     if (t < T) {
       const double o0 = __ldg(ocol + (size_t)s_x[t] * K);
-      chain_step(F, G, s_e + t * N, o0, i);
+      chain_step(si_tag, F, G, s_e + t * N, o0, i);
 #pragma unroll
       for (int j = 0; j < N; ++j) F[j] = G[j];
     }
     double lik = 0.0;
 #pragma unroll
     for (int j = 0; j < N; ++j) lik += F[j];
-    s_num[c] = s_pz[c] * lik;
+    return lik;
+  };
+  // chain -> thread map: the first N * KF chains (KF = K rounded down to whole warps) are laid out
+  // region-major with KF concepts per region, so every warp there works on ONE region; the
+  // (K - KF) * N left-over chains follow and take the generic path.
+  // (only for N <= 6: the 64-register budget of the 1024-thread launch bound has no room for the
+  // N-vector state of the larger specialisations)
+  const int KF = (N <= 6) ? (K & ~31) : 0;
+  for (int c = tid; c < N * K; c += blockDim.x) {
+    int i, k;
+    double lik;
+    if (c < N * KF) {
+      i = c / KF;
+      k = c - i * KF;
+      switch (i) {   // warp-uniform
+#define MWD_SI(V) \
+  case V:         \
+    if constexpr (V < N && N <= 6) lik = run_chain(std::integral_constant<int, V>{}, i, k); else lik = 0.0; \
+    break;
+        MWD_SI(0) MWD_SI(1) MWD_SI(2) MWD_SI(3) MWD_SI(4) MWD_SI(5) MWD_SI(6) MWD_SI(7)
+        MWD_SI(8) MWD_SI(9) MWD_SI(10) MWD_SI(11) MWD_SI(12) MWD_SI(13) MWD_SI(14) MWD_SI(15)
+#undef MWD_SI
+        default: lik = 0.0;
+      }
+    } else {
+      const int cc = c - N * KF, rem = K - KF;
+      i = cc / rem;
+      k = KF + (cc - i * rem);
+      lik = run_chain(std::integral_constant<int, -1>{}, i, k);
+    }
+    s_num[i * K + k] = s_pz[i * K + k] * lik;
   }
   __syncthreads();
   // row sums over k, one warp per region
