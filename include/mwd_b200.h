@@ -248,6 +248,20 @@ int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int given_alignment, 
                   double* align_probs, const int64_t* ap_off, int32_t* image_concepts,
                   double* cluster_scores, void* stream);
 
+/* printAlignment's two files -- image_phone_hmm_word_discoverer.py:620-648: HOST-side
+ * writer, byte-for-byte `'%d ' per phone + blank line` (.txt) and
+ * `json.dump(aligns, f, indent=4, sort_keys=True)` (.json, floats as float.__repr__) straight from the
+ * flat arrays of mwd_ik_decode.  All pointers [host], pairs in corpus order; phone_off / region_off:
+ * n_pairs+1 offsets; align_probs: (T x n) per pair at ap_off[p]; concept_alignment (Ttot),
+ * concept_probs (R x K, gaussian :651) and cluster_probs (R x K, two-layer) may be NULL -> key omitted. */
+int mwd_write_alignment_files(const char* txt_path, const char* json_path, int64_t n_pairs,
+                              const int64_t* phone_off, const int64_t* region_off, const int32_t* alignment,
+                              const int32_t* image_concepts, const int32_t* concept_alignment,
+                              const double* align_probs, const int64_t* ap_off, const double* concept_probs,
+                              const double* cluster_probs, int n_concepts, int is_phoneme);
+/* float.__repr__(v) into buf (NUL-terminated); returns the length or -1 (test hook of the writer) */
+int mwd_format_float_repr(double v, char* buf, int buf_len);
+
 /* argmax_k rows[t][k] (first index on ties, NaN-aware like np.argmax) -- printAlignment :628 */
 int mwd_argmax_rows(const double* rows, int64_t n_rows, int n_cols, int32_t* out, void* stream);
 

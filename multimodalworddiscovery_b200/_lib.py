@@ -109,6 +109,8 @@ SYMBOLS = {
     'mwd_ik_posterior_grad_finish': (_i, [_i, _i, _vp, _vp, _vp]),
     'mwd_ik_mstep': (_i, [C.POINTER(IkMstepArgs), _vp]),
     'mwd_ik_decode': (_i, [C.POINTER(IkProblem), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'mwd_write_alignment_files': (_i, [C.c_char_p, C.c_char_p, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    'mwd_format_float_repr': (_i, [_d, C.c_char_p, _i]),
     'mwd_argmax_rows': (_i, [_vp, _i64, _i, _vp, _vp]),
     'mwd_ik_forward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'mwd_ik_backward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

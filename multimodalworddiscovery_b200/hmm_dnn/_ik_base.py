@@ -8,6 +8,7 @@ while every per-caption computation runs as a CUDA kernel behind include/mwd_b20
 No NumPy/CPU fallback exists for the kernels: without the built library or a GPU, the methods
 that compute raise.
 """
+import ctypes as C
 import json
 import math
 import random
@@ -57,6 +58,64 @@ def one_hot_to_ids(aSen):
     if not (np.all(a[np.arange(len(ids)), ids] == 1.) and np.count_nonzero(a) == len(ids)):
         raise ValueError('aSen must be one-hot rows (soft phone posteriors are the image_audio classes)')
     return ids.astype(np.int32)
+
+
+def write_alignment_arrays(filePrefix, phone_off, region_off, ali, ic, ap, ap_off, concept_alignment=None,
+                           concept_probs=None, cluster_probs=None, n_concepts=0, is_phoneme=True):
+    """printAlignment's `.txt` + `.json` (:620-648) through the native writer of libmwd_b200.so
+    (csrc/align_json.cu) from FLAT corpus-order arrays: byte-identical to the reference's per-pair
+    dicts + ``json.dump(aligns, f, indent=4, sort_keys=True)``, without a Python object per number."""
+    lib = _lib.load()
+
+    def arr(a, dtype):
+        return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+    phone_off, region_off, ap_off = arr(phone_off, np.int64), arr(region_off, np.int64), arr(ap_off, np.int64)
+    ali, ic, ap = arr(ali, np.int32), arr(ic, np.int32), arr(ap, np.float64)
+    ca, cp, cl = arr(concept_alignment, np.int32), arr(concept_probs, np.float64), arr(cluster_probs, np.float64)
+    if ap.size != int(ap_off[-1]) or ali.size != int(phone_off[-1]) or ic.size != int(region_off[-1]):
+        raise ValueError('alignment arrays do not match their offsets')
+
+    def ptr(a):
+        return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+    _lib.check(lib.mwd_write_alignment_files((filePrefix + '.txt').encode(), (filePrefix + '.json').encode(),
+                                             len(phone_off) - 1, ptr(phone_off), ptr(region_off), ptr(ali), ptr(ic),
+                                             ptr(ca), ptr(ap), ptr(ap_off), ptr(cp), ptr(cl), int(n_concepts),
+                                             1 if is_phoneme else 0))
+
+
+def write_alignment_files(filePrefix, alis, ics, aps, concept_alignment=None, concept_probs=None,
+                          cluster_probs=None, n_concepts=0, is_phoneme=True):
+    """Same, from the per-pair lists the batched decode returns (corpus order)."""
+
+    def cat(rows, dtype):
+        if rows is None:
+            return None
+        rows = [np.asarray(r, dtype=dtype).ravel() for r in rows]
+        return np.concatenate(rows) if rows else np.zeros((0,), dtype=dtype)
+
+    T = np.array([len(a) for a in alis], dtype=np.int64)
+    n = np.array([len(c) for c in ics], dtype=np.int64)
+    write_alignment_arrays(filePrefix, np.concatenate([[0], np.cumsum(T)]), np.concatenate([[0], np.cumsum(n)]),
+                           cat(alis, np.int32), cat(ics, np.int32), cat(aps, np.float64),
+                           np.concatenate([[0], np.cumsum(T * n)]), cat(concept_alignment, np.int32),
+                           cat(concept_probs, np.float64), cat(cluster_probs, np.float64), n_concepts, is_phoneme)
+
+
+def ragged_to_corpus_order(flat, off, order, width=1):
+    """Rows stored in packed (sorted) order -> corpus order, vectorised.  ``off``: offsets (in rows) of the
+    packed pairs, ``order[s]`` = corpus index of packed pair s, ``width`` = entries per row.
+    Returns (flat in corpus order, offsets in corpus order)."""
+    off = np.asarray(off, dtype=np.int64)
+    L = np.diff(off)
+    inv = np.empty(len(order), dtype=np.int64)
+    inv[np.asarray(order, dtype=np.int64)] = np.arange(len(order), dtype=np.int64)
+    Lc = L[inv]
+    new_off = np.concatenate([[0], np.cumsum(Lc)]).astype(np.int64)
+    take = np.repeat(off[:-1][inv] - new_off[:-1], Lc) + np.arange(int(new_off[-1]), dtype=np.int64)
+    flat = np.asarray(flat).reshape(-1, width) if width > 1 else np.asarray(flat)
+    return flat[take], new_off
 
 
 class ImagePhoneHMMBase(object):
@@ -385,31 +444,45 @@ class ImagePhoneHMMBase(object):
 
     def printAlignment(self, filePrefix, isPhoneme=True, debug=False, _zero_concept_alignment=False):
         """:620-648 (gaussian adds 'concept_probs', :651)"""
+        rank, world = self._dist()
+        if world == 1:
+            return self._print_alignment_flat(filePrefix, isPhoneme, _zero_concept_alignment)
         alis, ics, aps, cas = self._decode_all(_zero_concept_alignment)
-        rank, _ = self._dist()
         if rank != 0:
             return
-        f = open(filePrefix + '.txt', 'w')
-        aligns = []
-        for i in range(len(self.vCorpus)):
-            n = len(ics[i])
-            align_info = {
-                'index': i,
-                'image_concepts': [int(c) for c in ics[i]],
-                'concept_alignment': [int(c) for c in cas[i]],
-                'alignment': [int(a) for a in alis[i]],
-                'align_probs': np.asarray(aps[i]).reshape(-1, n).tolist(),
-                'is_phoneme': isPhoneme
-            }
-            if self.GAUSSIAN:
-                align_info['concept_probs'] = np.asarray(self.conceptCounts[i]).tolist()
-            aligns.append(align_info)
-            for a in alis[i]:
-                f.write('%d ' % a)
-            f.write('\n\n')
-        f.close()
-        with open(filePrefix + '.json', 'w') as f:
-            json.dump(aligns, f, indent=4, sort_keys=True)
+        concept_probs = None
+        if self.GAUSSIAN:
+            concept_probs = [np.asarray(c, dtype=np.float64) for c in self.conceptCounts]
+        write_alignment_files(filePrefix, alis, ics, aps, concept_alignment=cas, concept_probs=concept_probs,
+                              n_concepts=self.nWords, is_phoneme=isPhoneme)
+
+    def _print_alignment_flat(self, filePrefix, isPhoneme, zero_concept_alignment):
+        """Single-process fast path: batched decode -> flat arrays -> corpus order -> native writer;
+        no per-pair Python objects (1 M pairs: seconds instead of the minutes of dict + json.dump)."""
+        eng = self._push()
+        ali, ic, ap = eng.decode(floor_norm=self.GAUSSIAN, want_probs=True, width=self._width())
+        pk = eng.pk
+        ali_c, phone_off = ragged_to_corpus_order(ali.cpu().numpy(), pk.phone_off, pk.order)
+        ic_c, region_off = ragged_to_corpus_order(ic.cpu().numpy(), pk.region_off, pk.order)
+        ap_c, ap_off = ragged_to_corpus_order(ap.cpu().numpy()[:int(pk.ap_offsets()[-1])], pk.ap_offsets(), pk.order)
+        if zero_concept_alignment:
+            ca_c = np.zeros(len(ali_c), dtype=np.int32)
+        else:
+            if not getattr(self, '_cA_valid', False):       # AttributeError before any trainUsingEM (:628)
+                raise AttributeError("'%s' object has no attribute 'conceptCountsA'" % type(self).__name__)
+            if getattr(self, '_conceptCountsA_cache', None) is not None:
+                ca_c = np.concatenate([np.argmax(c, axis=1) for c in self._conceptCountsA_cache])
+            else:
+                ca_c, _ = ragged_to_corpus_order(eng.concept_alignment().cpu().numpy(), pk.phone_off, pk.order)
+        cp_c = None
+        if self.GAUSSIAN:
+            if getattr(self, '_conceptCounts_cache', None) is not None:
+                cp_c = np.concatenate([np.asarray(c, dtype=np.float64) for c in self._conceptCounts_cache]).ravel()
+            else:
+                cp_c, _ = ragged_to_corpus_order(eng.cC[:pk.n_regions].cpu().numpy(), pk.region_off, pk.order,
+                                                 width=self.nWords)
+        write_alignment_arrays(filePrefix, phone_off, region_off, ali_c, ic_c, ap_c, ap_off, concept_alignment=ca_c,
+                               concept_probs=cp_c, n_concepts=self.nWords, is_phoneme=isPhoneme)
 
     # ------------------------------------------------------------------ simulated annealing
     def simulatedAnnealing(self, numIterations=100, T0=0.5, stepScale=5., debug=False):

@@ -21,7 +21,7 @@ from scipy.special import logsumexp
 import random
 from copy import deepcopy
 
-from ._ik_base import ImagePhoneHMMBase
+from ._ik_base import ImagePhoneHMMBase, write_alignment_files
 
 NULL = "NULL"
 DEBUG = False
@@ -209,24 +209,7 @@ class ImageAudioHMMWordDiscoverer(ImagePhoneHMMBase):
     rank, _ = self._dist()
     if rank != 0:
       return
-    f = open(filePrefix+'.txt', 'w')
-    aligns = []
-    for i in range(len(self.vCorpus)):
-      n = len(ics[i])
-      align_info = {
-            'index': i,
-            'image_concepts': [int(c) for c in ics[i]],
-            'alignment': [int(a) for a in alis[i]],
-            'align_probs': np.asarray(aps[i]).reshape(-1, n).tolist(),
-            'is_phoneme': isPhoneme
-          }
-      aligns.append(align_info)
-      for a in alis[i]:
-        f.write('%d ' % a)
-      f.write('\n\n')
-    f.close()
-    with open(filePrefix+'.json', 'w') as f:
-      json.dump(aligns, f, indent=4, sort_keys=True)
+    write_alignment_files(filePrefix, alis, ics, aps, n_concepts=self.nWords, is_phoneme=isPhoneme)
 
   def simulatedAnnealing(self, numIterations=100, T0=0.5, stepScale=5., debug=False):
     """:157-192.  The reference snapshots ``self.W`` (:173), an attribute this class does not have."""

@@ -10,7 +10,7 @@ from scipy.special import logsumexp
 import random
 from copy import deepcopy
 
-from ._ik_base import ImagePhoneHMMBase, OneHotCorpus, one_hot_to_ids
+from ._ik_base import write_alignment_files, ImagePhoneHMMBase, OneHotCorpus, one_hot_to_ids
 
 NULL = "NULL"
 DEBUG = False
@@ -147,26 +147,9 @@ class ImagePhoneHMMDNNWordDiscoverer(ImagePhoneHMMBase):
     rank, _ = self._dist()
     if rank != 0:
       return
-    f1 = open(filePrefix + '.txt', 'w')
-    f2 = open(filePrefix + '_clusters.txt', 'w')
-    aligns = []
-    for i in range(len(self.vCorpus)):
-      n = len(ics[i])
-      aligns.append({
-            'index': i,
-            'image_concepts': [int(c) for c in ics[i]],
-            'alignment': [int(a) for a in alis[i]],
-            'cluster_probs': np.asarray(css[i]).tolist(),
-            'align_probs': np.asarray(aps[i]).reshape(-1, n).tolist(),
-            'is_phoneme': isPhoneme
-          })
-      for a in alis[i]:
-        f1.write('%d ' % a)
-      f1.write('\n\n')
-      for c in ics[i]:
-        f2.write('%d ' % c)
-      f2.write('\n\n')
-    f1.close()
-    f2.close()
-    with open(filePrefix + '.json', 'w') as f:
-      json.dump(aligns, f, indent=4, sort_keys=True)
+    write_alignment_files(filePrefix, alis, ics, aps, cluster_probs=css, n_concepts=self.nWords,
+                          is_phoneme=isPhoneme)
+    with open(filePrefix + '_clusters.txt', 'w') as f2:
+      for i in range(len(self.vCorpus)):
+        f2.write(''.join('%d ' % c for c in ics[i]))
+        f2.write('\n\n')
