@@ -100,6 +100,11 @@ typedef struct {
                                 (s_t, floor-sum, xi diagonal, r_t; n each) handed from the
                                 recursion kernel to the count post-pass                      */
   const int64_t* slot_off;   /* [dev] N+1: slot_off[p] = sum_{q<p} T_q * n_q                */
+  int32_t no_floor;          /* 0: reference EPS floors (all classes but one); 1: the un-floored
+                                normalisers of ImageAudioGaussianHMMWordDiscoverer
+                                (image_audio_gaussian_hmm_word_discoverer.py:369-371,414-415,449-451,
+                                :629-631): likelihood, gamma and xi are divided by their raw sums   */
+  int32_t reserved0;
 } mwd_ik_problem;
 
 /* bytes of `scratch` mwd_ik_estep needs for this problem (depends on t_max, bucket_n, K) */
@@ -216,6 +221,8 @@ int mwd_ik_posterior_grad_finish(int n_concepts, int feat_dim, const double* gra
 #define MWD_MSTEP_FLOOR_TABLES 1   /* EPS-floor init/trans counts (gaussian and two-layer classes)   */
 #define MWD_MSTEP_NO_POSTERIOR 2  /* leave posterior_param alone (two-layer: mwd_sgd_update instead)*/
 #define MWD_MSTEP_FREEZE_TRANS 4  /* trainUsingEM(freezeTransition=True) of the two-layer class     */
+#define MWD_MSTEP_NO_FLOORS 8     /* un-floored init / trans / phone-table normalisers even when gaussian
+                                     (image_audio_gaussian_hmm_word_discoverer.py:241-260)           */
 typedef struct {
   int32_t gaussian;          /* 0 linear (W), 1 gaussian (mus; implies FLOOR_TABLES)        */
   int32_t n_concepts, n_phone_types, feat_dim;

@@ -37,7 +37,7 @@ class IkProblem(C.Structure):
         ('pair_ll', C.c_void_p), ('concept_counts_a', C.c_void_p),
         ('part_phone', C.c_void_p), ('part_init', C.c_void_p), ('part_trans', C.c_void_p),
         ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64),
-        ('stats', C.c_void_p), ('slot_off', C.c_void_p),
+        ('stats', C.c_void_p), ('slot_off', C.c_void_p), ('no_floor', C.c_int32), ('reserved0', C.c_int32),
     ]
 
 

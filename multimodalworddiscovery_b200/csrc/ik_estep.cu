@@ -65,6 +65,7 @@ ik_estep_kernel(const EstepArgs a) {
   constexpr int KS = KG * kLanesPerRow;
   const int n = (NN > 0) ? NN : a.n;
   const int K = a.K, B = a.B;
+  const double eps = a.eps;
   const int tid = threadIdx.x;
   const int l8 = tid & 7;
   const int grp = tid >> 3;
@@ -201,7 +202,7 @@ ik_estep_kernel(const EstepArgs a) {
           if (i == 0 && l8 == 0) {
             double L = 0.0;
             for (int j = 0; j < n; ++j) L += ex[j];
-            L = floor_eps(L);
+            L = floor_at(L, a.eps);
             a.pair_ll[pair] = log(L);                              // :529
             // sum_{i,k} alpha_t beta_t equals the sentence likelihood at every t, so the floored
             // normaliser of updateStateCounts (:430) is one constant per pair
@@ -279,7 +280,7 @@ ik_estep_kernel(const EstepArgs a) {
             double beta = last ? 1.0 : fma(d_i, bo[j], w);
             dg = fma(av, bo[j], dg);
             double g = av * beta;
-            sumF += kv ? floor_eps(g) : 0.0;
+            sumF += kv ? floor_at(g, eps) : 0.0;
             double o = kv ? __ldg(orow + 8 * j) : 0.0;
             bo[j] = beta * o;
             rr = fma(bo[j], pz[j], rr);
@@ -375,6 +376,7 @@ struct CountsArgs {
   double* part_trans;
   int64_t lo, hi;
   int n, total_warps;
+  double eps;            // xi floor (MWD_EPS or 0)
 };
 
 __device__ __forceinline__ double warp_sum_all(double v) {
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(256) ik_counts_kernel(const CountsArgs a) {
           if (q < epl && lane + 32 * q < nn) {
             const double u = __ldcg(row + off_a[q]);
             const double xi = (coef[q] < 0.0) ? u : (u * coef[q]) * __ldcg(nxt + off_b[q]);
-            xv[q] = floor_eps(xi);
+            xv[q] = floor_at(xi, a.eps);
             z += xv[q];
           }
         }
@@ -468,6 +470,7 @@ __global__ void __launch_bounds__(256) ik_counts_kernel(const CountsArgs a) {
 // in registers, so a (pair, t) step costs ~10 warp-instructions instead of ~100.
 template <int N>
 __global__ void __launch_bounds__(256) ik_counts_small_kernel(const CountsArgs a) {
+  const double eps = a.eps;
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   double aoff[N * N];
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(256) ik_counts_small_kernel(const CountsArgs a
 #pragma unroll
           for (int c = 0; c < N; ++c) {
             const double xi = (r == c) ? dgv[r] : (sv[r] * aoff[r * N + c]) * rn[c];    // :388-389
-            xv[r * N + c] = floor_eps(xi);                                             // :396
+            xv[r * N + c] = floor_at(xi, eps);                                            // :396
             z += xv[r * N + c];
           }
         const double iz = 1.0 / z;
@@ -715,6 +718,7 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     a.NC = pl.NC;
     a.Tmax = p->bucket_tmax[b];
     a.ll_only = ll_only;
+    a.eps = p->no_floor ? 0.0 : MWD_EPS;
     int rc = 0;
     if (use_warp) rc = estep_warp_launch(a, st);
     else switch (pl.KG) {
@@ -738,6 +742,7 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
       c.lo = lo;
       c.hi = hi;
       c.n = n;
+      c.eps = a.eps;
       c.total_warps = estep_grid_rows() * 8;     // one partial row per CTA, 8 warps per CTA
       switch (n) {
         case 1: ik_counts_small_kernel<1><<<estep_grid_rows(), 256, 0, st>>>(c); break;

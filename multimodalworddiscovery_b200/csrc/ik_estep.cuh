@@ -26,6 +26,7 @@ struct EstepArgs {
   int64_t cta_scratch;   // doubles per CTA
   int n, K, P, B, NC, Tmax;
   int ll_only;           // 1: forward sweep + log-likelihood only
+  double eps;            // floor of the likelihood / gamma / xi normalisers: MWD_EPS, or 0 (un-floored classes)
 };
 
 // Warp-per-pair kernel (ik_estep_warp.cu).  estep_warp_supported: true when an instantiation exists

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
   constexpr int KC = (KS0 + 31) / 32;                            // columns per lane in the column pass
   const int K = a.K;
   const int B = RB ? 2 : a.B;
+  const double eps = a.eps;
   const int lane = threadIdx.x & 31;
   const int wic = threadIdx.x >> 5;
   const int gw = blockIdx.x * kWpc + wic;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
           double L = 0.0;
 #pragma unroll
           for (int jp = 0; jp < N; ++jp) L += sv[jp];
-          L = floor_eps(L);
+          L = floor_at(L, eps);
           if (lane == 0) a.pair_ll[pair] = log(L);                       // :529
           // sum_{i,k} alpha_t beta_t equals the sentence likelihood at every t, so the floored
           // normaliser of updateStateCounts (:430) is one constant per pair
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kerne
         const bool kv = (q < KG - 1) ? on : kv_last;
         const double beta = fma(d_i, bo[q], w);
         const double g = av[q] * beta;
-        const double f = kv ? floor_eps(g) : 0.0;
+        const double f = kv ? floor_at(g, eps) : 0.0;
         if (q & 1) {
           dg_b = fma(av[q], bo[q], dg_b);
           sumF_b += f;

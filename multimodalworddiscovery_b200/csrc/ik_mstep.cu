@@ -132,12 +132,12 @@ __global__ void mstep_init_trans_kernel(LensArg la, int gaussian, int toeplitz, 
 }
 
 // obsT[p][k] = phoneC[p][k] / sum_p max(phoneC[p][k], EPS)    (:255-256)
-__global__ void mstep_obs_kernel(const double* __restrict__ phoneC, int P, int K,
+__global__ void mstep_obs_kernel(const double* __restrict__ phoneC, int P, int K, double eps,
                                  double* __restrict__ obsT) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   double norm = 0.0;
-  for (int p = 0; p < P; ++p) norm += floor_eps(phoneC[(size_t)p * K + k]);
+  for (int p = 0; p < P; ++p) norm += floor_at(phoneC[(size_t)p * K + k], eps);
   for (int p = 0; p < P; ++p) obsT[(size_t)p * K + k] = phoneC[(size_t)p * K + k] / norm;
 }
 
@@ -208,11 +208,12 @@ extern "C" int mwd_ik_mstep(const mwd_ik_mstep_args* a, void* stream) {
   const double* phoneC = a->counts;
   const double* initC = a->counts + pe;
   const double* transC = a->counts + pe + ie;
-  const int floor_tables = (a->gaussian || (a->flags & MWD_MSTEP_FLOOR_TABLES)) ? 1 : 0;
+  const int no_floors = (a->flags & MWD_MSTEP_NO_FLOORS) ? 1 : 0;
+  const int floor_tables = (!no_floors && (a->gaussian || (a->flags & MWD_MSTEP_FLOOR_TABLES))) ? 1 : 0;
   mstep_init_trans_kernel<<<a->n_lens, 256, 0, st>>>(la, floor_tables, a->toeplitz,
                                                      (a->flags & MWD_MSTEP_FREEZE_TRANS) ? 1 : 0, initC, transC,
                                                      a->init, a->trans);
-  mstep_obs_kernel<<<(K + 127) / 128, 128, 0, st>>>(phoneC, P, K, a->obsT);
+  mstep_obs_kernel<<<(K + 127) / 128, 128, 0, st>>>(phoneC, P, K, no_floors ? -1.0 : kEps, a->obsT);
   const double invN = 1.0 / (double)a->n_pairs_global;
   if (a->flags & MWD_MSTEP_NO_POSTERIOR) {
     MWD_CHECK_LAUNCH();

@@ -45,6 +45,10 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 // np.maximum(x, EPS): NaN propagates (fmax would swallow it)
 __device__ __forceinline__ double floor_eps(double x) { return (x < kEps) ? kEps : x; }
+// same with a run-time floor: EPS, or 0 for the classes whose counts are NOT floored
+// (image_audio_gaussian_hmm_word_discoverer.py:369-371,414-415,449-451) -- on probabilities a
+// floor of 0 is the identity, so the un-floored mode costs no extra instruction
+__device__ __forceinline__ double floor_at(double x, double eps) { return (x < eps) ? eps : x; }
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int mask) {
   return __shfl_xor_sync(0xffffffffu, v, mask);
