@@ -255,7 +255,7 @@ class IKEngine(object):
     def mstep(self, lr, momentum, width=1.0, freeze_trans=False):
         a = IkMstepArgs()
         a.gaussian = 1 if self.gaussian else 0
-        a.flags = (3 if self.two_layer else 0) | (4 if freeze_trans else 0)   # MWD_MSTEP_* bits
+        a.flags = (3 if self.two_layer else 0) | (4 if freeze_trans else 0) | getattr(self, '_mstep_extra_flags', 0)   # MWD_MSTEP_* bits
         a.n_concepts, a.n_phone_types, a.feat_dim = self.K, self.P, self.D
         a.n_lens, a.lens = len(self._lens), _np_ptr(self._lens)
         a.toeplitz = self.toeplitz

@@ -13,6 +13,8 @@ so every recursion below is the image-phone one evaluated with ``obs = E.T`` and
 What is new: ``updateConceptPhoneCounts`` (:486-493), the phone-probability M-step (:250-251) and
 the audio posterior update (:527-541).
 """
+import math
+
 import numpy as np
 
 from . import image_phone_hmm as ip
@@ -150,4 +152,128 @@ def cluster(v, a, params, alignment):
     """cluster, :649-661."""
     pz = ip.posterior_linear(v, params['WV'])
     _, E = emissions(a, params['WA'], params['phone_probs'])
+    return ip.cluster(pz, np.arange(a.shape[0]), np.ascontiguousarray(E.T), alignment)
+
+
+# ==============================================================================================
+# ImageAudioGaussianHMMWordDiscoverer -- hmm_dnn/image_audio_gaussian_hmm_word_discoverer.py
+# RBF posteriors on both sides (:573-595) and NO EPS floor anywhere in the E- or M-step
+# (:241-260, :369-371, :414-415, :449-451, :629-631); align keeps its floors (:646-648).
+# ==============================================================================================
+def emissions_gaussian(a, musA, width, phone_probs):
+    """softmaxLayerA :585-595 and probs_x_given_z :304."""
+    ph = ip.posterior_gaussian(a, musA, width)
+    return ph, (phone_probs @ ph.T).T
+
+
+def init_counts_raw(fwd, bwd):
+    """updateInitialCounts :362-372 -- un-floored."""
+    g = fwd * bwd
+    return np.sum(g.sum(-1) / g.sum((1, 2))[:, None], axis=0)
+
+
+def trans_counts_raw(fwd, bwd, pz, E, A, toeplitz):
+    """updateTransitionCounts :388-433 -- un-floored normalisation."""
+    T, n = fwd.shape[0], fwd.shape[1]
+    d = np.diag(A)
+    Aoff = A - np.diag(d)
+    out = np.zeros((n, n))
+    for t in range(T - 1):
+        o = E[t + 1]
+        xi = np.diag(np.sum(fwd[t] * d[:, None] * o * bwd[t + 1], axis=-1))
+        xi = xi + fwd[t].sum(-1)[:, None] * Aoff * np.sum(pz * o * bwd[t + 1], axis=-1)
+        xi = xi / np.sum(xi)
+        if toeplitz:
+            xi = ip.toeplitz_pool(xi)
+        out += xi
+    return out
+
+
+def estep_pair_gaussian(v, a, params):
+    n, T = v.shape[0], a.shape[0]
+    pz = ip.posterior_gaussian(v, params['musV'], params['width'])
+    ph, E = emissions_gaussian(a, params['musA'], params['width'], params['phone_probs'])
+    x = np.arange(T)
+    obs = np.ascontiguousarray(E.T)
+    pi, A = params['init'][n], params['trans'][n]
+    fwd = ip.forward(pz, x, obs, pi, A)
+    bwd = ip.backward(pz, x, obs, A)
+    cpc = concept_phone_counts(fwd, bwd, ph)
+    return dict(pz=pz, ph=ph, E=E, ll=math.log(float(np.sum(fwd[-1]))),             # :629-631
+                init=init_counts_raw(fwd, bwd),
+                trans=trans_counts_raw(fwd, bwd, pz, E, A, params['toeplitz']),
+                cpc=cpc, cC=ip.concept_counts(pz, x, obs, pi, A))
+
+
+def em_iteration_gaussian(feats, audio, params):
+    """One epoch body of trainUsingEM (:203-268), is_exact = False."""
+    K, nPh = params['phone_probs'].shape
+    N = len(feats)
+    lens = sorted(params['init'].keys())
+    initC = {m: np.zeros((m,)) for m in lens}
+    transC = {m: np.zeros((m, m)) for m in lens}
+    phoneC = np.zeros((K, nPh))
+    cC_all, pz_all, ph_all, cpc_all = [], [], [], []
+    ll = 0.0
+    for v, a in zip(feats, audio):
+        r = estep_pair_gaussian(v, a, params)
+        n = v.shape[0]
+        ll += r['ll']
+        initC[n] += r['init']
+        transC[n] += r['trans']
+        phoneC += np.sum(r['cpc'], axis=0)
+        cC_all.append(r['cC'])
+        pz_all.append(r['pz'])
+        ph_all.append(r['ph'])
+        cpc_all.append(r['cpc'])
+    new = dict(params)
+    new['init'], new['trans'] = {}, {}
+    for m in lens:
+        new['init'][m] = initC[m] / np.sum(initC[m])                          # :243
+        tot = np.sum(transC[m], axis=1)                                       # :248
+        tr = params['trans'][m].copy()
+        for s in range(m):
+            if tot[s] != 0:
+                tr[s] = transC[m][s] / tot[s]
+        new['trans'][m] = tr
+    new['phone_probs'] = (phoneC.T / np.sum(phoneC, axis=-1)).T               # :260-261
+    lr, mom, width = params['lr'], params['momentum'], params['width']
+    dV = np.zeros_like(params['musV'])                                        # updateSoftmaxWeightV :529-538
+    for v, cC, pz in zip(feats, cC_all, pz_all):
+        Delta = cC - pz
+        dV += 1.0 / (N * width) * (Delta.T @ v - (np.sum(Delta, axis=0) * params['musV'].T).T)
+    new['musV'] = (1.0 - mom) * params['musV'] + lr * dV
+    dA = np.zeros_like(params['musA'])                                        # updateSoftmaxWeightA :551-558
+    for a, cpc, ph in zip(audio, cpc_all, ph_all):
+        Delta = np.sum(cpc, axis=1) - ph
+        dA += 1.0 / (N * width) * (Delta.T @ a - (np.sum(Delta, axis=0) * params['musA'].T).T)
+    new['musA'] = (1.0 - mom) * params['musA'] + lr * dA
+    info = dict(avg_ll=ll / N, initC=initC, transC=transC, phoneC=phoneC, cC=cC_all, cpc=cpc_all, ph=ph_all, dA=dA)
+    return new, info
+
+
+def initial_params_gaussian(feats, n_words, n_phones, musV, musA, width=1.0, lr=10.0, momentum=0.0,
+                            phone_probs=None):
+    lens = sorted({v.shape[0] for v in feats})
+    return dict(
+        init={m: np.ones((m,)) / m for m in lens},
+        trans={m: np.ones((m, m)) / m for m in lens},
+        phone_probs=(np.ones((n_words, n_phones)) / n_phones) if phone_probs is None
+        else np.array(phone_probs, dtype=float),
+        musV=np.array(musV, dtype=float), musA=np.array(musA, dtype=float), width=width,
+        lr=lr, momentum=momentum, toeplitz=len(lens) >= 6)
+
+
+def align_gaussian(v, a, params):
+    """align :633-664 (floored like the linear class)."""
+    pz = ip.posterior_gaussian(v, params['musV'], params['width'])
+    _, E = emissions_gaussian(a, params['musA'], params['width'], params['phone_probs'])
+    n = v.shape[0]
+    return ip.align(pz, np.arange(a.shape[0]), np.ascontiguousarray(E.T), params['init'][n], params['trans'][n],
+                    floor_norm=True, floor_scores=True)
+
+
+def cluster_gaussian(v, a, params, alignment):
+    pz = ip.posterior_gaussian(v, params['musV'], params['width'])
+    _, E = emissions_gaussian(a, params['musA'], params['width'], params['phone_probs'])
     return ip.cluster(pz, np.arange(a.shape[0]), np.ascontiguousarray(E.T), alignment)

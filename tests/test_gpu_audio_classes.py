@@ -114,3 +114,62 @@ def test_image_audio_matches_oracle_beyond_30_pairs(tmp_path):
         np.testing.assert_allclose(pp, p['phone_probs'], rtol=RTOL)
         np.testing.assert_allclose(WV, p['WV'], rtol=1e-8, atol=1e-12)
         np.testing.assert_allclose(eng.get_audio_param(), p['WA'], rtol=RTOL, atol=1e-15)
+
+
+@pytest.mark.parametrize('case', ['short', 'mixed', 'long_unfloored'])
+def test_image_audio_gaussian_class_matches_reference(case, tmp_path):
+    """ImageAudioGaussianHMMWordDiscoverer: RBF posteriors on both sides, NO EPS floors (the long case has
+    raw likelihoods ~1e-165, far below EPS, and still normalised counts)."""
+    from multimodalworddiscovery_b200.hmm_dnn.image_audio_gaussian_hmm_word_discoverer import \
+        ImageAudioGaussianHMMWordDiscoverer
+    g = dict(np.load(os.path.join(GOLDEN, 'iag_%s.npz' % case)))
+    fo, ao = g['feat_off'], g['audio_off']
+    feats = [g['feats'][fo[i]:fo[i + 1]] for i in range(len(fo) - 1)]
+    audio = [g['audio'][ao[i]:ao[i + 1]] for i in range(len(ao) - 1)]
+    tmp = str(tmp_path)
+    np.savez(os.path.join(tmp, 'v.npz'), **{'arr_%d' % i: v for i, v in enumerate(feats)})
+    np.savez(os.path.join(tmp, 'a.npz'), **{'arr_%d' % i: a for i, a in enumerate(audio)})
+    np.save(os.path.join(tmp, 'mv.npy'), g['musV0'])
+    np.save(os.path.join(tmp, 'ma.npy'), g['musA0'])
+    cfg = dict(n_words=int(g['K']), n_phones=int(g['nPh']), learning_rate=float(g['lr']), momentum=float(g['momentum']),
+               width=float(g['width']), visual_anchor_file=os.path.join(tmp, 'mv.npy'),
+               audio_anchor_file=os.path.join(tmp, 'ma.npy'), feature_dtype='float64')
+    if 'pp0' in g:
+        np.save(os.path.join(tmp, 'pp.npy'), g['pp0'])
+        cfg['phone_prob_file'] = os.path.join(tmp, 'pp.npy')
+    m = ImageAudioGaussianHMMWordDiscoverer(os.path.join(tmp, 'a.npz'), os.path.join(tmp, 'v.npz'), cfg,
+                                            modelName=os.path.join(tmp, 'm'))
+    assert len(m.vCorpus) == len(feats)
+    m.initializeModel()
+    assert os.path.exists(os.path.join(tmp, 'm.json'))              # printUnimodalCluster (:150)
+    lens = [int(v) for v in g['lens']]
+    for it in range(int(g['n_iter'])):
+        m.trainUsingEM(1, warmStart=True, printStatus=True)
+        ll = np.load(os.path.join(tmp, 'm_likelihoods.npy'))[0]
+        np.testing.assert_allclose(ll, g['avg_ll'][it], rtol=RTOL)
+        np.testing.assert_allclose(flatten_tables(lens, m.init), g['init_%d' % it], rtol=RTOL)
+        np.testing.assert_allclose(flatten_tables(lens, m.trans), g['trans_%d' % it], rtol=RTOL)
+        np.testing.assert_allclose(m.phoneProbs, g['pp_%d' % it], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(m.musV, g['musV_%d' % it], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(m.musA, g['musA_%d' % it], rtol=RTOL, atol=1e-15)
+        np.testing.assert_allclose(np.concatenate(m.conceptCounts, axis=0), g['cC_%d' % it], rtol=RTOL, atol=1e-300)
+    cpc = m.conceptPhoneCounts
+    assert cpc[0].shape == (len(audio[0]), int(g['K']), int(g['nPh']))
+    np.testing.assert_allclose(cpc[0].sum((1, 2)), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(m.computeAvgLogLikelihood(), float(g['final_ll']), rtol=RTOL)
+    m.printAlignment(os.path.join(tmp, 'ali'))
+    with open(os.path.join(tmp, 'ali.json')) as f:
+        ali = json.load(f)
+    assert sorted(ali[0].keys()) == [str(k) for k in g['ali_keys']]
+    for key in ('alignment', 'image_concepts', 'phone_clusters', 'concept_alignment'):
+        assert np.array_equal(np.concatenate([a[key] for a in ali]), g[key]), key
+    np.testing.assert_allclose(np.concatenate([np.array(a['align_probs']).ravel() for a in ali]), g['align_probs'],
+                               rtol=1e-8)
+    np.testing.assert_allclose(np.concatenate([np.array(a['concept_probs']).ravel() for a in ali]),
+                               g['concept_probs'], rtol=RTOL, atol=1e-300)
+    v0, a0 = m.vCorpus[0], m.aCorpus[0]
+    np.testing.assert_allclose(m.forward(v0, a0), g['fwd0'], rtol=RTOL)
+    np.testing.assert_allclose(m.backward(v0, a0), g['bwd0'], rtol=RTOL)
+    path, _ = m.align(a0, v0)
+    assert path == ali[0]['alignment']
+    assert m.cluster(a0, v0, path)[0] == ali[0]['image_concepts']

@@ -21,16 +21,18 @@ from hmm_dnn.image_phone_hmm_word_discoverer import *
 from hmm_dnn.image_phone_hmm_dnn_word_discoverer import *      # run_image2phone.py:2
 from hmm_dnn.image_phone_gaussian_hmm_word_discoverer import *
 from hmm_dnn.image_audio_hmm_word_discoverer import *          # run_image2audio.py:9
-from hmm_dnn.image_audio_gaussian_hmm_word_discoverer import * # run_image2audio.py -- reference file (not mirrored)
+from hmm_dnn.image_audio_gaussian_hmm_word_discoverer import * # run_image2audio.py:10
+from hmm_dnn.image_phone_bhmm_word_discoverer import *          # reference file (not mirrored)
 from hmm.hmm_word_discoverer import *
 from hmm.audio_segembed_hmm_word_discoverer import *
 from hmm.audio_hmm_word_discoverer import *
 from utils.clusteval import *               # reference module; needs the nltk / matplotlib stubs
 from utils.postprocess import *
 for cls in (ImagePhoneHMMWordDiscoverer, ImagePhoneGaussianHMMWordDiscoverer, HMMWordDiscoverer, AudioHMMWordDiscoverer,
-            SegEmbedHMMWordDiscoverer, ImagePhoneHMMDNNWordDiscoverer, ImageAudioHMMWordDiscoverer):
+            SegEmbedHMMWordDiscoverer, ImagePhoneHMMDNNWordDiscoverer, ImageAudioHMMWordDiscoverer,
+            ImageAudioGaussianHMMWordDiscoverer):
     assert cls.__module__.startswith('multimodalworddiscovery_b200.'), cls.__module__
-assert ImageAudioGaussianHMMWordDiscoverer.__module__ == 'hmm_dnn.image_audio_gaussian_hmm_word_discoverer'
+assert ImagePhoneBigramHMMWordDiscoverer.__module__ == 'hmm_dnn.image_phone_bhmm_word_discoverer'
 assert np.__name__ == 'numpy' and json.__name__ == 'json'   # names the drivers rely on (run_image2phone.py:132,137)
 print('OK')
 ''' % REF
