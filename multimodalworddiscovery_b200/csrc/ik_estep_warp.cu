@@ -29,6 +29,10 @@ namespace mwd {
 
 constexpr int kWpc = 4;            // warps per CTA
 constexpr int kWarpCtasPerSm = 3;  // 12 warps per SM (register budget 65536 / 384 = 170)
+// concepts per lane above which the register-resident lattice needs the 255-register budget of
+// 2 CTAs (8 warps) per SM: n = 7..10 at K = 65, n = 5..6 at K = 100
+constexpr int kWarpBigKG = 14;
+constexpr int warp_ctas_per_sm(int KG) { return KG >= kWarpBigKG ? 2 : kWarpCtasPerSm; }
 constexpr int kWBmax = 8;          // max checkpoint interval
 
 // L2 residency hints: the alpha checkpoints are the only global data with reuse (written in the
@@ -71,7 +75,7 @@ __device__ __forceinline__ double row_sum_head(double v, int j) {
 // stays in registers, so alpha never touches shared memory (only the gamma slice does, for the
 // column sums) and o_{t+1} is loaded once for the recompute and the backward step.
 template <int N, int KG, bool OBS_S, bool RB>
-__global__ void __launch_bounds__(kWpc * 32, kWarpCtasPerSm) ik_estep_warp_kernel(const EstepArgs a) {
+__global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp_kernel(const EstepArgs a) {
   constexpr int LPR = 32 / N;
   constexpr int ROWL = N * LPR;                                  // lanes that own lattice rows
   constexpr int KS0 = LPR * KG;                                  // concepts per row incl. padding
@@ -373,7 +377,8 @@ struct WarpPlan {
 // run_image2phone.py:73 / image_phone_hmm_word_discoverer.py:735) for the n they are fast for.
 #define MWD_WARP_COMBOS(X)                                                              \
   X(1, 2) X(1, 3) X(1, 4) X(2, 4) X(2, 5) X(2, 7) X(3, 5) X(3, 7) X(3, 10) X(4, 7) X(4, 9) \
-  X(4, 13) X(5, 9) X(5, 11) X(6, 10) X(6, 13)
+  X(4, 13) X(5, 9) X(5, 11) X(6, 10) X(6, 13)                                             \
+  X(5, 17) X(7, 13) X(7, 17) X(8, 13) X(8, 17) X(9, 17) X(9, 22) X(10, 17) X(10, 22)
 // register-block variant: compiled (and the default) for the MSCOCO shape, where it measured
 // 55.1 vs 60.3 ms at 1M pairs; MWD_ESTEPW_RB=0 selects the shared-memory block variant instead
 #define MWD_WARP_RB_COMBOS(X) X(5, 11)
@@ -396,14 +401,15 @@ static bool warp_enabled() {
 }
 
 static bool plan_warp(int n, int K, int P, int Tmax, int64_t npairs, WarpPlan* pl) {
-  if (n < 1 || n > 6 || !warp_enabled()) return false;
+  if (n < 1 || n > 10 || !warp_enabled()) return false;
   const int lpr = 32 / n;
   pl->KG = warp_kg(n, K);
   if (!warp_combo(n, pl->KG)) return false;
   const int ks0 = lpr * pl->KG;
   const int ks = ks0 + (((lpr - ks0) % 16) + 16) % 16;
   const size_t slice = (size_t)kWpc * n * ks * sizeof(double);     // one alpha slice of every warp of a CTA
-  size_t budget = (size_t)224 * 1024 / kWarpCtasPerSm - 1024;
+  const int cps = warp_ctas_per_sm(pl->KG);
+  size_t budget = (size_t)224 * 1024 / cps - 1024;
   // emission table in shared memory when it leaves room for a checkpoint interval of >= 3
   const size_t obs_bytes = (((size_t)P * K + 1) & ~(size_t)1) * sizeof(double);
   pl->obs_s = (obs_bytes + 3 * slice <= budget) ? 1 : 0;
@@ -415,7 +421,7 @@ static bool plan_warp(int n, int K, int P, int Tmax, int64_t npairs, WarpPlan* p
 #undef X
   if (const char* e = getenv("MWD_ESTEPW_RB")) { if (atoi(e) == 0) pl->rb = 0; }
   if (pl->rb) {   // register block: B = 2, two gamma slices per warp, table in shared memory if it fits
-    pl->obs_s = (obs_bytes + 2 * slice <= (size_t)224 * 1024 / kWarpCtasPerSm - 1024) ? 1 : 0;
+    pl->obs_s = (obs_bytes + 2 * slice <= (size_t)224 * 1024 / cps - 1024) ? 1 : 0;
     budget = 2 * slice;
   }
   int B = (int)(budget / slice);
@@ -427,7 +433,7 @@ static bool plan_warp(int n, int K, int P, int Tmax, int64_t npairs, WarpPlan* p
   pl->NC = (Tmax + B - 1) / B;
   if (pl->NC < 1) pl->NC = 1;
   pl->smem = (size_t)B * slice + (pl->obs_s ? obs_bytes : 0);
-  int ctas_per_sm = kWarpCtasPerSm;
+  int ctas_per_sm = cps;
   if (const char* e = getenv("MWD_ESTEPW_CTAS")) { int v = atoi(e); if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v; }
   int64_t grid = (int64_t)sm_count() * ctas_per_sm;
   const int64_t need = (npairs + kWpc - 1) / kWpc;
