@@ -28,7 +28,6 @@
 namespace mwd {
 
 
-constexpr int NQ = 1;   // exchanged per-row quantity: s_t (forward) / r_t (backward)
 constexpr int BMAX = 8; // max checkpoint interval
 constexpr int kEPP = 4; // pairs per CTA
 
