@@ -293,6 +293,11 @@ def gpu_arm(args):
     del sh['feats'], sh['phones']
     torch.cuda.empty_cache()
     eng = IKEngine(pk, K_CONCEPTS, P_PHONES, gaussian=False, device=dev, keep_concept_counts_a=False)
+    if args.chunks <= 0:
+        # enough chunks to overlap the PCIe copy with the kernels, not so many that a small corpus
+        # drowns in launches (1 M pairs: 10.4 GB -> 16 chunks; MSCOCO-2k: 21 MB -> 1 chunk)
+        shard_bytes = sum(host[k].numel() * host[k].element_size() for k in host)
+        args.chunks = int(min(16, max(1, shard_bytes // (640 << 20))))
 
     # initializeModel(): uniform init/trans/obs, injected W  (parameter snapshot restored every step)
     init = {m: np.ones(m) / m for m in pk.lens}
@@ -439,7 +444,8 @@ def main():
     ap.add_argument('--variant', default='coco5', choices=['coco5', 'coco10'])
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--chunks', type=int, default=16, help='chunks of the streamed (e2e) iteration')
+    ap.add_argument('--chunks', type=int, default=0,
+                    help='chunks of the streamed (e2e) iteration (0 = one per ~640 MB of shard, at most 16)')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)
