@@ -384,6 +384,19 @@ def gpu_arm(args):
         dist.all_reduce(tot)
         h2d, d2h = int(tot[0]), int(tot[1])
 
+    # ---- align leg ("plus align-pairs/s separately"): batched Viterbi + cluster of the whole
+    # shard under the current parameters (posterior GEMM + K6), alignments written to HBM
+    restore()
+    for _ in range(2):
+        eng.decode(want_probs=False)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eng.decode(want_probs=False)
+    e1.record()
+    barrier()
+    ms_align = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
     if rank == 0:
         T_mean = pk.n_phones_total / max(pk.n_pairs, 1)
         n_mean = pk.n_regions / max(pk.n_pairs, 1)
@@ -426,6 +439,13 @@ def gpu_arm(args):
                               'peak': fp64_peak, 'unit': 'TFLOP/s per GPU', 'frac': args.pairs * fpp / (ms_step * 1e-3) / 1e12 / world / fp64_peak,
                               'algorithmic_flop_per_pair': fpp,
                               'peak_source': 'profiles/r01_fp64_peak_microbench.txt (measured DFMA = DMMA = 37.0)'},
+            'gemm_roofline': {'bound': 'fp64 tensor path (DMMA m8n8k4)', 'kernel': 'posterior',
+                              'achieved': 2.0 * pk.n_regions * (D_FEAT + 1) * K_CONCEPTS / (kern_ms['posterior'] * 1e-3) / 1e12,
+                              'peak': fp64_peak, 'unit': 'TFLOP/s',
+                              'frac': 2.0 * pk.n_regions * (D_FEAT + 1) * K_CONCEPTS / (kern_ms['posterior'] * 1e-3) / 1e12 / fp64_peak,
+                              'note': 'regions x concepts emission GEMM + row softmax; ncu: profiles/r01_ncu_full_summary_k1w.txt'},
+            'align': {'value': args.pairs / (ms_align * 1e-3), 'unit': 'pairs/s', 'ms_per_pass': ms_align,
+                      'what': 'align + cluster of every pair (posterior GEMM + Viterbi kernel), resident'},
             'cpu_baseline': cpu_baseline,
             'clocks': clock_info,
         }
