@@ -37,105 +37,147 @@ __device__ __forceinline__ bool np_greater(double cand, double best) {
   return (cand > best) || (cand != cand && best == best);
 }
 
-__global__ void __launch_bounds__(128) ik_decode_kernel(const DecodeArgs a) {
-  const int64_t pair = blockIdx.x;
-  const int tid = threadIdx.x;
+// One WARP owns one pair (persistent warps, fixed pair -> warp stride): no block barriers, the
+// Viterbi scores live in lanes j < n and travel by shuffles, back-pointers / marginal emissions /
+// the alignment sit in the warp's private shared-memory slab.  Arithmetic order is unchanged from
+// the reference: sequential-k FMA chain for p[t][i], (scores[i]*A[i][j])*p[t][j] scanned in i with
+// strict '>', products of cluster() in t order.
+constexpr int kDecWarps = 4;   // warps per CTA
+
+// NN > 0: every pair of the launch has n == NN regions (one launch per bucket; the state loops unroll
+// without predicates); NN == 0: n is read per pair (single-pair calls, n > 10).
+template <int NN>
+__global__ void __launch_bounds__(kDecWarps * 32) ik_decode_kernel(const DecodeArgs a, int64_t lo, int64_t hi, int nmax,
+                                                                   int slab_bytes) {
+  constexpr int NU = NN > 0 ? NN : kNMax;      // unroll bound of the state loops
+  const int lane = threadIdx.x & 31;
+  const int wic = threadIdx.x >> 5;
   const int K = a.K;
-  const int p0 = a.phone_off[pair];
-  const int T = a.phone_off[pair + 1] - p0;
-  const int64_t r0 = a.region_off[pair];
-  const int n = (int)(a.region_off[pair + 1] - r0);
-  const int32_t* ph = a.phones + p0;
-
   extern __shared__ double smem[];
-  double* s_pz = smem;                              // [n][K]
-  double* s_p = s_pz + kNMax * K;                   // [Tmax][n]
-  double* s_sc = s_p + (size_t)a.Tmax * kNMax;      // [2][NMAX]
-  int* s_x = reinterpret_cast<int*>(s_sc + 2 * kNMax);     // [Tmax]
-  unsigned char* s_bp = reinterpret_cast<unsigned char*>(s_x) + (((size_t)a.Tmax * sizeof(int) + 7) & ~(size_t)7);  // [Tmax][NMAX]
-  // cluster scores [n][K] live in their own region after the back-pointers (8-byte aligned)
-  double* s_cl = reinterpret_cast<double*>(s_bp + (((size_t)a.Tmax * kNMax + 7) & ~(size_t)7));
+  unsigned char* slab = reinterpret_cast<unsigned char*>(smem) + (size_t)wic * slab_bytes;
+  double* s_pz = reinterpret_cast<double*>(slab);                    // [nmax][K]  pz, later cluster scores
+  double* s_p = s_pz + (size_t)nmax * K;                             // [Tmax][nmax] marginal emissions
+  int* s_x = reinterpret_cast<int*>(s_p + (size_t)a.Tmax * nmax);    // [Tmax] phone ids
+  int* s_ali = s_x + a.Tmax;                                         // [Tmax] alignment
+  unsigned char* s_bp = reinterpret_cast<unsigned char*>(s_ali + a.Tmax);   // [Tmax][nmax] back-pointers
 
-  for (int e = tid; e < n * K; e += blockDim.x) s_pz[e] = a.pz[r0 * K + e];
-  for (int t = tid; t < T; t += blockDim.x) s_x[t] = ph[t];
-  __syncthreads();
-  // p[t][i] = sum_k pz[i][k] obs[k][x_t]   (:550)
-  for (int e = tid; e < T * n; e += blockDim.x) {
-    int t = e / n, i = e - t * n;
-    const double* orow = a.obsT + (size_t)s_x[t] * K;
-    const double* prow = s_pz + i * K;
-    double acc = 0.0;
-    for (int k = 0; k < K; ++k) acc = fma(prow[k], __ldg(orow + k), acc);
-    s_p[t * n + i] = acc;
-  }
-  __syncthreads();
-
-  const double* A = a.trans + (size_t)n * MWD_TRANS_STRIDE;
-  const double* pi = a.init + (size_t)n * MWD_INIT_STRIDE;
-  double* ap = a.align_probs ? a.align_probs + a.ap_off[pair] : nullptr;
-
-  if (tid < 32 && !a.given_alignment) {
-    const int j = tid;
-    double sc = 0.0;
-    if (j < n) {
-      sc = pi[j] * s_p[j];                                       // :555
-      s_sc[j] = sc;
-      if (ap) ap[j] = sc;                                        // :559 (raw, un-normalised)
-    }
+  const int64_t gw = (int64_t)blockIdx.x * kDecWarps + wic;
+  const int64_t nwarps = (int64_t)gridDim.x * kDecWarps;
+  for (int64_t pair = lo + gw; pair < hi; pair += nwarps) {
+    const int p0 = a.phone_off[pair];
+    const int T = a.phone_off[pair + 1] - p0;
+    const int64_t r0 = a.region_off[pair];
+    const int n = NN > 0 ? NN : (int)(a.region_off[pair + 1] - r0);
+    const int32_t* ph = a.phones + p0;
+    __syncwarp();   // the previous pair's slab is no longer read
+    for (int e = lane; e < n * K; e += 32) s_pz[e] = a.pz[r0 * K + e];
+    for (int t = lane; t < T; t += 32) s_x[t] = ph[t];
+    if (a.given_alignment)
+      for (int t = lane; t < T; t += 32) s_ali[t] = a.alignment[p0 + t];
     __syncwarp();
-    int cur = 0;
-    for (int t = 1; t < T; ++t) {
-      const double* prev = s_sc + ((t - 1) & 1) * kNMax;
-      double* next = s_sc + (t & 1) * kNMax;
-      if (j < n) {
-        const double pt = s_p[t * n + j];
-        double best = __dmul_rn(__dmul_rn(prev[0], A[j]), pt);   // (scores[i]*A[i][j])*p[t][j]
-        int arg = 0;
-        for (int i = 1; i < n; ++i) {
-          double cand = __dmul_rn(__dmul_rn(prev[i], A[i * n + j]), pt);
-          if (np_greater(cand, best)) { best = cand; arg = i; }
+    const double* A = a.trans + (size_t)n * MWD_TRANS_STRIDE;
+    const double* pi = a.init + (size_t)n * MWD_INIT_STRIDE;
+    double* ap = a.align_probs ? a.align_probs + a.ap_off[pair] : nullptr;
+
+    if (!a.given_alignment) {
+      // p[t][i] = sum_k pz[i][k] obs[k][x_t]   (:550), one (t,i) item per lane
+      // (four items per lane in flight: each item is a K-long dependent FMA chain)
+      for (int e0 = lane; e0 < T * n; e0 += 128) {
+        const double* orow[4];
+        const double* prow[4];
+        double acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = min(e0 + 32 * u, T * n - 1);
+          const int t = e / n, i = e - t * n;
+          orow[u] = a.obsT + (size_t)s_x[t] * K;
+          prow[u] = s_pz + i * K;
+          acc[u] = 0.0;
         }
-        s_bp[t * kNMax + j] = (unsigned char)arg;                // :562
-        sc = (a.floor_norm & 2) ? best : floor_eps(best);        // :564 (two-layer :612 does not floor)
-        next[j] = sc;
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fma(prow[u][k], __ldg(orow[u] + k), acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (e0 + 32 * u < T * n) s_p[e0 + 32 * u] = acc[u];
       }
       __syncwarp();
-      if (ap && j < n) {
-        double tot = 0.0;
-        for (int i = 0; i < n; ++i) tot += (a.floor_norm & 1) ? floor_eps(next[i]) : next[i];
-        ap[(size_t)t * n + j] = sc / tot;                        // :571 / gaussian :583
+      const int j = lane;
+      const bool on = j < n;
+      double acol[NU];                       // A[i][j], i < n
+#pragma unroll
+      for (int i = 0; i < NU; ++i) acol[i] = (on && i < n) ? A[i * n + j] : 0.0;
+      double sc = on ? pi[j] * s_p[j] : 0.0;                         // :555
+      if (ap && on) ap[j] = sc;                                      // :559 (raw, un-normalised)
+      for (int t = 1; t < T; ++t) {
+        const double pt = on ? s_p[t * n + j] : 0.0;
+        double best = 0.0;
+        int arg = 0;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          if (NN > 0 || i < n) {                                     // warp-uniform
+            const double prev = __shfl_sync(0xffffffffu, sc, i);
+            const double cand = __dmul_rn(__dmul_rn(prev, acol[i]), pt);   // (scores[i]*A[i][j])*p[t][j]
+            if (i == 0 || np_greater(cand, best)) { best = cand; arg = i; }
+          }
+        }
+        if (on) s_bp[t * n + j] = (unsigned char)arg;                // :562
+        sc = (a.floor_norm & 2) ? best : floor_eps(best);            // :564 (two-layer :612 does not floor)
+        if (ap) {                                                    // warp-uniform
+          double tot = 0.0;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            if (NN > 0 || i < n) {
+              const double v = __shfl_sync(0xffffffffu, sc, i);
+              tot += (a.floor_norm & 1) ? floor_eps(v) : v;
+            }
+          }
+          if (on) ap[(size_t)t * n + j] = sc / tot;                  // :571 / gaussian :583
+        }
       }
-    }
-    if (j == 0) {
-      const double* fin = s_sc + ((T - 1) & 1) * kNMax;
-      double best = fin[0];
-      for (int i = 1; i < n; ++i)
-        if (np_greater(fin[i], best)) { best = fin[i]; cur = i; }
-      a.alignment[p0 + T - 1] = cur;                             // :576-582
-      for (int t = T - 1; t > 0; --t) {
-        cur = s_bp[t * kNMax + cur];
-        a.alignment[p0 + t - 1] = cur;
+      // final argmax over states (first index on ties), then the back-trace by lane 0
+      int cur = 0;
+      {
+        double best = __shfl_sync(0xffffffffu, sc, 0);
+#pragma unroll
+        for (int i = 1; i < NU; ++i) {
+          if (NN > 0 || i < n) {
+            const double v = __shfl_sync(0xffffffffu, sc, i);
+            if (np_greater(v, best)) { best = v; cur = i; }
+          }
+        }
       }
+      __syncwarp();                                                  // back-pointers visible to lane 0
+      if (lane == 0) {
+        s_ali[T - 1] = cur;                                          // :576-582
+        for (int t = T - 1; t > 0; --t) {
+          cur = s_bp[t * n + cur];
+          s_ali[t - 1] = cur;
+        }
+      }
+      __syncwarp();
+      for (int t = lane; t < T; t += 32) a.alignment[p0 + t] = s_ali[t];
     }
-  }
-  __syncthreads();
-  // cluster (:586-597): scores[i][k] = pz[i][k] * prod_{t: align[t]==i} obs[k][x_t], in t order
-  for (int e = tid; e < n * K; e += blockDim.x) {
-    int i = e / K, k = e - i * K;
-    double sc = s_pz[e];
-    for (int t = 0; t < T; ++t)
-      if (a.alignment[p0 + t] == i) sc = __dmul_rn(sc, __ldg(a.obsT + (size_t)s_x[t] * K + k));
-    s_cl[e] = sc;
-    if (a.cluster_scores) a.cluster_scores[r0 * K + e] = sc;
-  }
-  __syncthreads();
-  if (tid < n) {
-    const double* row = s_cl + tid * K;
-    double best = row[0];
-    int arg = 0;
-    for (int k = 1; k < K; ++k)
-      if (np_greater(row[k], best)) { best = row[k]; arg = k; }
-    a.image_concepts[r0 + tid] = arg;
+    // cluster (:586-597): scores[i][k] = pz[i][k] * prod_{t: align[t]==i} obs[k][x_t], in t order
+    // time-major: step t multiplies the K scores of the aligned region by obs[:, x_t] (lanes over k);
+    // every (i,k) product still runs in t order, each lane only ever touches its own columns
+    for (int t = 0; t < T; ++t) {
+      double* row = s_pz + s_ali[t] * K;
+      const double* orow = a.obsT + (size_t)s_x[t] * K;
+      for (int k = lane; k < K; k += 32) row[k] = __dmul_rn(row[k], __ldg(orow + k));
+    }
+    __syncwarp();
+    if (a.cluster_scores)
+      for (int e = lane; e < n * K; e += 32) a.cluster_scores[r0 * K + e] = s_pz[e];
+    if (lane < n) {
+      const double* row = s_pz + lane * K;
+      double best = row[0];
+      int arg = 0;
+      for (int k = 1; k < K; ++k)
+        if (np_greater(row[k], best)) { best = row[k]; arg = k; }
+      a.image_concepts[r0 + lane] = arg;
+    }
   }
 }
 
@@ -269,15 +311,46 @@ extern "C" int mwd_ik_decode(const mwd_ik_problem* p, int floor_norm, int given_
   a.floor_norm = floor_norm;
   a.given_alignment = given_alignment;
   a.cluster_scores = cluster_scores;
-  // s_pz [NMAX][K] | s_p [Tmax][NMAX] | s_sc [2][NMAX] | s_x [Tmax] ints | s_bp [Tmax][NMAX] bytes | s_cl [NMAX][K]
-  size_t smem = ((size_t)kNMax * a.K + (size_t)a.Tmax * kNMax + 2 * kNMax) * sizeof(double) +
-                (((size_t)a.Tmax * sizeof(int) + 7) & ~(size_t)7) + (((size_t)a.Tmax * kNMax + 7) & ~(size_t)7) +
-                (size_t)kNMax * a.K * sizeof(double);
+  // per-warp slab: s_pz [nmax][K] | s_p [Tmax][nmax] doubles | s_x, s_ali [Tmax] ints | s_bp [Tmax][nmax] bytes
+  int nmax = 0;
+  for (int b = 0; b < p->n_buckets; ++b)
+    if (p->bucket_lo[b + 1] > p->bucket_lo[b] && p->bucket_n[b] > nmax) nmax = p->bucket_n[b];
+  if (nmax <= 0 || nmax > kNMax) nmax = kNMax;          // no bucket descriptors (single-pair calls)
+  const int Tm = a.Tmax > 0 ? a.Tmax : 1;
+  a.Tmax = Tm;
+  size_t slab = ((size_t)nmax * a.K + (size_t)Tm * nmax) * sizeof(double) + (size_t)2 * Tm * sizeof(int) +
+                (size_t)Tm * nmax;
+  slab = (slab + 15) & ~(size_t)15;
+  const size_t smem = slab * kDecWarps;
   MWD_REQUIRE(smem <= 227 * 1024, "decode shared memory %zu exceeds 227 KB (t_max=%d)", smem, a.Tmax);
-  if (smem > 48 * 1024)
-    MWD_CHECK_CUDA(cudaFuncSetAttribute(ik_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-  ik_decode_kernel<<<(unsigned)p->n_pairs, 128, smem, st>>>(a);
+  int per_sm = (int)((size_t)224 * 1024 / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 16 / kDecWarps * 4) per_sm = 16 / kDecWarps * 4;    // at most 64 warps per SM
+  auto launch = [&](auto kern, int64_t lo, int64_t hi) -> int {
+    if (smem > 48 * 1024)
+      MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    const int64_t need = (hi - lo + kDecWarps - 1) / kDecWarps;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, kDecWarps * 32, smem, st>>>(a, lo, hi, nmax, (int)slab);
+    return 0;
+  };
+  if (p->n_buckets <= 0) {
+    int rc = launch(ik_decode_kernel<0>, 0, p->n_pairs);
+    if (rc) return rc;
+  }
+  for (int b = 0; b < p->n_buckets; ++b) {
+    const int64_t lo = p->bucket_lo[b], hi = p->bucket_lo[b + 1];
+    if (hi <= lo) continue;
+    int rc;
+    switch (p->bucket_n[b]) {
+#define MWD_DN(V) case V: rc = launch(ik_decode_kernel<V>, lo, hi); break;
+      MWD_DN(1) MWD_DN(2) MWD_DN(3) MWD_DN(4) MWD_DN(5) MWD_DN(6) MWD_DN(7) MWD_DN(8) MWD_DN(9) MWD_DN(10)
+#undef MWD_DN
+      default: rc = launch(ik_decode_kernel<0>, lo, hi); break;
+    }
+    if (rc) return rc;
+  }
   MWD_CHECK_LAUNCH();
   return 0;
 }
