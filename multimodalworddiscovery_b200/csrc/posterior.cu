@@ -37,12 +37,16 @@ __device__ __forceinline__ double load_feat(const FT* p) { return (double)__ldg(
 // run; the fp32->fp64 conversion happens only when the registers are staged into shared memory.
 // EPI 0: + bias, row softmax (image posterior);  EPI 1: + bias, ReLU (hidden layer of the two-layer
 // class, hmm_dnn/image_phone_hmm_dnn_word_discoverer.py:573-579).  ldo = row stride of the output.
-template <int NT, int MT, typename FT, int EPI>
+// TAIL: K == 8*NT + 1 (the MSCOCO concept count 65 = 8*8 + 1): the last concept column is not padded
+// to a ninth 8-wide DMMA tile (11 % of the tensor work for one column) but accumulated with plain
+// DFMAs from the A fragments the lanes already hold -- lane (g4,l4) has V[row m*8+g4][kk*4+l4], i.e.
+// the 4 lanes of a group cover the chunk of a row; their partial dot products are summed in the epilogue.
+template <int NT, int MT, typename FT, int EPI, bool TAIL = false>
 __global__ void __launch_bounds__(256, (NT * MT <= 18) ? 2 : 1)
 posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* __restrict__ W,
                  int K, double* __restrict__ pz, int ldo) {
   constexpr int BM = 64 * MT;
-  constexpr int KP = 8 * NT;
+  constexpr int KP = 8 * NT + (TAIL ? 1 : 0);
   __shared__ double sV[BM * LDS_PAD];
   __shared__ double sW[KP * LDS_PAD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -55,6 +59,9 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
   for (int m = 0; m < MT; ++m)
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[m][j][0] = acc[m][j][1] = 0.0;
+  double tail[MT];                           // partial logits of concept 8*NT (TAIL)
+#pragma unroll
+  for (int m = 0; m < MT; ++m) tail[m] = 0.0;
 
   constexpr int VPT = BM / 16;               // V elements per thread per chunk (row = tid/16 + 16 q)
   constexpr int WPT = (KP + 15) / 16;        // W elements per thread per chunk (k   = tid/16 + 16 q)
@@ -110,8 +117,20 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
       for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int j = 0; j < NT; ++j) dmma(acc[m][j][0], acc[m][j][1], af[m], bf[j]);
+      if (TAIL) {
+        const double wt = sW[(8 * NT) * LDS_PAD + kk * 4 + l4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tail[m] = fma(af[m], wt, tail[m]);
+      }
     }
     __syncthreads();
+  }
+  if (TAIL) {   // the 4 lanes of a group hold the partial sums of one row: every lane gets the total
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      tail[m] += __shfl_xor_sync(0xffffffffu, tail[m], 1);
+      tail[m] += __shfl_xor_sync(0xffffffffu, tail[m], 2);
+    }
   }
   // epilogue: + bias, exp(x - logsumexp(x)) per row (scipy.special.logsumexp is max-shifted).
   // Fragment layout: lane holds row g4, columns j*8 + l4*2 + {0,1}; the 4 lanes l4=0..3 of a
@@ -131,6 +150,10 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
             pz[gr * ldo + k] = (x > 0.0) ? x : 0.0;
           }
         }
+      if (TAIL && l4 == 0) {
+        const double x = tail[m] + __ldg(W + (size_t)(8 * NT) * ldw + D);
+        pz[gr * ldo + 8 * NT] = (x > 0.0) ? x : 0.0;
+      }
     }
     return;
   }
@@ -147,6 +170,10 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
           mx = fmax(mx, acc[m][j][h]);
         }
       }
+    if (TAIL) {
+      tail[m] += __ldg(W + (size_t)(8 * NT) * ldw + D);
+      mx = fmax(mx, tail[m]);
+    }
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     double sum = 0.0;
@@ -157,6 +184,7 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
         int k = j * 8 + l4 * 2 + h;
         if (k < K) sum += exp(acc[m][j][h] - mx);
       }
+    if (TAIL && l4 == 0) sum += exp(tail[m] - mx);    // counted once per row
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     const double lse = log(sum) + mx;
@@ -169,6 +197,7 @@ posterior_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* _
           int k = j * 8 + l4 * 2 + h;
           if (k < K) pz[gr * ldo + k] = exp(acc[m][j][h] - lse);
         }
+      if (TAIL && l4 == 0) pz[gr * ldo + 8 * NT] = exp(tail[m] - lse);
     }
   }
 }
@@ -195,7 +224,7 @@ __global__ void gaussian_expand_kernel(const double* __restrict__ mus, int K, in
   }
 }
 
-template <int NT, int EPI>
+template <int NT, int EPI, bool TAIL = false>
 static int launch_posterior(const void* feats, int is64, int64_t R, int D, const double* W, int K,
                             double* pz, int ldo, cudaStream_t st) {
   if (R <= 0) return 0;
@@ -203,9 +232,9 @@ static int launch_posterior(const void* feats, int is64, int64_t R, int D, const
   int64_t grid = (R + 64 * MT - 1) / (64 * MT);
   MWD_REQUIRE(grid <= 0x7fffffff, "too many regions for one launch");
   if (is64)
-    posterior_kernel<NT, MT, double, EPI><<<(unsigned)grid, 256, 0, st>>>((const double*)feats, R, D, W, K, pz, ldo);
+    posterior_kernel<NT, MT, double, EPI, TAIL><<<(unsigned)grid, 256, 0, st>>>((const double*)feats, R, D, W, K, pz, ldo);
   else
-    posterior_kernel<NT, MT, float, EPI><<<(unsigned)grid, 256, 0, st>>>((const float*)feats, R, D, W, K, pz, ldo);
+    posterior_kernel<NT, MT, float, EPI, TAIL><<<(unsigned)grid, 256, 0, st>>>((const float*)feats, R, D, W, K, pz, ldo);
   MWD_CHECK_LAUNCH();
   return 0;
 }
@@ -214,6 +243,9 @@ template <int EPI>
 static int posterior_dispatch_epi(const void* feats, int is64, int64_t R, int D, const double* W, int K,
                                   double* pz, int ldo, cudaStream_t st) {
   MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "%d output columns outside [1,%d]", K, MWD_KMAX);
+  // K = 8*NT + 1 for the concept counts in use (65 = MSCOCO, 33 = tests): tail-column variant
+  if (K == 65) return launch_posterior<8, EPI, true>(feats, is64, R, D, W, K, pz, ldo, st);
+  if (K == 33) return launch_posterior<4, EPI, true>(feats, is64, R, D, W, K, pz, ldo, st);
   switch ((K + 7) / 8) {
 #define MWD_NT(T) case T: return launch_posterior<T, EPI>(feats, is64, R, D, W, K, pz, ldo, st);
     MWD_NT(1) MWD_NT(2) MWD_NT(3) MWD_NT(4) MWD_NT(5) MWD_NT(6) MWD_NT(7) MWD_NT(8)
@@ -239,13 +271,15 @@ static int posterior_dispatch(const void* feats, int is64, int64_t R, int D, con
 constexpr int BD = 128;
 constexpr int BR = 16;
 
-template <int MT8, typename FT>
+// TAIL: K == 8*MT8 + 1: the last Delta row is accumulated with DFMAs against the B fragments instead of
+// padding a ninth m-tile (see posterior_kernel).
+template <int MT8, typename FT, bool TAIL = false>
 __global__ void __launch_bounds__(256, (MT8 <= 9) ? 2 : 1)
 posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const double* __restrict__ cC,
                       const double* __restrict__ pz, int ldc, int K, int64_t rows_per_split,
                       double* __restrict__ partial, int accumulate) {
-  constexpr int KP = 8 * MT8;
-  constexpr int LDD = KP + 4;            // Delta tile [BR][KP], padded: 608 B == 96 mod 128 (KP=72)
+  constexpr int KP = 8 * MT8 + (TAIL ? 1 : 0);
+  constexpr int LDD = 8 * (MT8 + (TAIL ? 1 : 0)) + 4;   // Delta tile [BR][KP], padded: 608 B == 96 mod 128 (KP=72)
   constexpr int LDV = BD + 4;            // V tile [BR][BD], padded: 1056 B == 32 mod 128
   __shared__ double sDl[BR * LDD];
   __shared__ double sV[BR * LDV];
@@ -264,6 +298,7 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[m][j][0] = acc[m][j][1] = 0.0;
   double bias_acc = 0.0;
+  double tail[2] = {0.0, 0.0};           // TAIL: partial grad[8*MT8][warp*16 + j*8 + g4] over r == l4 (mod 4)
 
   // Delta tile: BR*KP elements, thread handles element e = tid + 256 q -> (row e / KP, k e % KP)
   constexpr int DPT = (BR * KP + 255) / 256;
@@ -318,6 +353,11 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
 #pragma unroll
         for (int j = 0; j < 2; ++j) dmma(acc[m][j][0], acc[m][j][1], af, bf[j]);
       }
+      if (TAIL) {
+        const double dt = sDl[(kk * 4 + l4) * LDD + 8 * MT8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tail[j] = fma(dt, bf[j], tail[j]);
+      }
     }
     if (do_bias && tid < KP) {
 #pragma unroll
@@ -341,6 +381,18 @@ posterior_grad_kernel(const FT* __restrict__ feats, int64_t R, int D, const doub
           *o = accumulate ? (*o + acc[m][j][h]) : acc[m][j][h];
         }
       }
+  }
+  if (TAIL) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      tail[j] += __shfl_xor_sync(0xffffffffu, tail[j], 1);
+      tail[j] += __shfl_xor_sync(0xffffffffu, tail[j], 2);
+      const int d = d0 + warp * 16 + j * 8 + g4;
+      if (l4 == 0 && d < D) {
+        double* o = out + (size_t)(8 * MT8) * ld + d;
+        *o = accumulate ? (*o + tail[j]) : tail[j];
+      }
+    }
   }
   if (do_bias && tid < K) {
     double* o = out + (size_t)tid * ld + D;
@@ -371,7 +423,7 @@ static int grad_splits_for(int D) {
   return kGradSplits * m;
 }
 
-template <int MT8>
+template <int MT8, bool TAIL = false>
 static int launch_grad(const GradIn& g, double* partial, int accumulate, cudaStream_t st) {
   const int D = g.D, K = g.K;
   const int64_t R = g.R;
@@ -381,10 +433,10 @@ static int launch_grad(const GradIn& g, double* partial, int accumulate, cudaStr
   if (rps < BR) rps = BR;
   dim3 grid((D + BD - 1) / BD, splits);
   if (g.feat_is_f64)
-    posterior_grad_kernel<MT8, double><<<grid, 256, 0, st>>>((const double*)g.feats, R, D, g.delta, g.minus,
+    posterior_grad_kernel<MT8, double, TAIL><<<grid, 256, 0, st>>>((const double*)g.feats, R, D, g.delta, g.minus,
                                                              g.ldc, K, rps, partial, accumulate);
   else
-    posterior_grad_kernel<MT8, float><<<grid, 256, 0, st>>>((const float*)g.feats, R, D, g.delta, g.minus,
+    posterior_grad_kernel<MT8, float, TAIL><<<grid, 256, 0, st>>>((const float*)g.feats, R, D, g.delta, g.minus,
                                                             g.ldc, K, rps, partial, accumulate);
   MWD_CHECK_LAUNCH();
   return 0;
@@ -429,6 +481,8 @@ static int grad_generic(const GradIn& g, double* grad_partials, int accumulate, 
   const int K = g.K;
   MWD_REQUIRE(K >= 1 && K <= MWD_KMAX, "%d gradient rows outside [1,%d]", K, MWD_KMAX);
   int rc = 2;
+  if (K == 65) return launch_grad<8, true>(g, grad_partials, accumulate, st);
+  if (K == 33) return launch_grad<4, true>(g, grad_partials, accumulate, st);
   switch ((K + 7) / 8) {
 #define MWD_MT(T) case T: rc = launch_grad<T>(g, grad_partials, accumulate, st); break;
     MWD_MT(1) MWD_MT(2) MWD_MT(3) MWD_MT(4) MWD_MT(5) MWD_MT(6) MWD_MT(7) MWD_MT(8)
