@@ -443,7 +443,7 @@ def gpu_arm(args):
                               'achieved': 2.0 * pk.n_regions * (D_FEAT + 1) * K_CONCEPTS / (kern_ms['posterior'] * 1e-3) / 1e12,
                               'peak': fp64_peak, 'unit': 'TFLOP/s',
                               'frac': 2.0 * pk.n_regions * (D_FEAT + 1) * K_CONCEPTS / (kern_ms['posterior'] * 1e-3) / 1e12 / fp64_peak,
-                              'note': 'regions x concepts emission GEMM + row softmax; ncu: profiles/r01_ncu_full_summary_k1w.txt'},
+                              'note': 'regions x concepts emission GEMM + row softmax; ncu: profiles/r01_ncu_full_summary_final.txt'},
             'align': {'value': args.pairs / (ms_align * 1e-3), 'unit': 'pairs/s', 'ms_per_pass': ms_align,
                       'what': 'align + cluster of every pair (posterior GEMM + Viterbi kernel), resident'},
             'cpu_baseline': cpu_baseline,

@@ -198,6 +198,8 @@ ik_estep_kernel(const EstepArgs a) {
       if (act) {
         const double* ex = s_exch + exo;
         if (t == T - 1) {
+          // negative sentinel in the (unused) s slot of the last row: see ik_counts_small_kernel
+          if (l8 == 0 && !a.ll_only) __stcg(my_stats + (t * 4 + 0) * n, -1.0);
           if (i == 0 && l8 == 0) {
             double L = 0.0;
             for (int j = 0; j < n; ++j) L += ex[j];
@@ -480,24 +482,31 @@ __global__ void __launch_bounds__(256) ik_counts_small_kernel(const CountsArgs a
   for (int e = 0; e < N * N; ++e) acc_t[e] = 0.0;
 #pragma unroll
   for (int e = 0; e < N; ++e) acc_i[e] = 0.0;
-  for (int64_t pair = a.lo + gw; pair < a.hi; pair += a.total_warps) {
-    const int T = a.phone_off[pair + 1] - a.phone_off[pair];
-    const double* st = a.stats + 4 * a.slot_off[pair];
-    for (int t = lane; t < T; t += 32) {
-      const double* row = st + (size_t)t * 4 * N;
+  // Row-parallel: the bucket's (pair, t) rows are contiguous in `stats` (4N doubles each); every warp
+  // takes one contiguous chunk of rows, a lane one row at a time -- no per-pair metadata, full lanes.
+  // A pair's last row carries a negative sentinel in its s slot (no xi there).
+  const int64_t s_lo = a.slot_off[a.lo], rows = (a.slot_off[a.hi] - s_lo) / N;   // slots = T*n per pair
+  const double* base = a.stats + 4 * s_lo;
+  const int64_t chunk = (rows + a.total_warps - 1) / a.total_warps;
+  const int64_t g_end = min(rows, (int64_t)(gw + 1) * chunk);
+  for (int64_t g = (int64_t)gw * chunk + lane; g < g_end; g += 32) {
+    {
+      const double* row = base + (size_t)g * 4 * N;
       double f[N], Ft = 0.0;
 #pragma unroll
-      for (int r = 0; r < N; ++r) { f[r] = __ldcg(row + N + r); Ft += f[r]; }
+      for (int r = 0; r < N; ++r) { f[r] = __ldcs(row + N + r); Ft += f[r]; }
       const double iF = 1.0 / Ft;
 #pragma unroll
       for (int r = 0; r < N; ++r) acc_i[r] = fma(f[r], iF, acc_i[r]);                 // :355
-      if (t < T - 1) {
-        double sv[N], dgv[N], rn[N], xv[N * N], z = 0.0;
+      double sv[N];
+#pragma unroll
+      for (int r = 0; r < N; ++r) sv[r] = __ldcs(row + r);
+      if (!(sv[0] < 0.0) && g + 1 < rows) {
+        double dgv[N], rn[N], xv[N * N], z = 0.0;
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-          sv[r] = __ldcg(row + r);
-          dgv[r] = __ldcg(row + 2 * N + r);
-          rn[r] = __ldcg(row + 4 * N + 3 * N + r);
+          dgv[r] = __ldcs(row + 2 * N + r);
+          rn[r] = __ldcs(row + 4 * N + 3 * N + r);
         }
 #pragma unroll
         for (int r = 0; r < N; ++r)

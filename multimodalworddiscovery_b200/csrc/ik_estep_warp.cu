@@ -189,6 +189,9 @@ __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp
           for (int jp = 0; jp < N; ++jp) L += sv[jp];
           L = floor_at(L, eps);
           if (lane == 0) a.pair_ll[pair] = log(L);                       // :529
+        // s_{T-1} is never used by the counts; a negative sentinel marks the pair's last row for the
+        // row-parallel count post-pass (ik_counts_small_kernel)
+        if (head && !a.ll_only) __stcs(st + (t * 4 + 0) * N, -1.0);
           // sum_{i,k} alpha_t beta_t equals the sentence likelihood at every t, so the floored
           // normaliser of updateStateCounts (:430) is one constant per pair
           inorm = 1.0 / L;

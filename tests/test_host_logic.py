@@ -120,3 +120,23 @@ def test_class_constructs_on_cpu_and_compute_fails_loudly(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(_lib.MwdError):
             m.computeAvgLogLikelihood()
+
+
+def test_pack_audio_pairs_shards_cover_the_corpus():
+    """engine_audio.pack_audio_pairs: frames follow the (n, T)-sorted order of their pairs, the identity
+    phone sequence indexes them, and the round-robin shards of two ranks partition the corpus."""
+    from multimodalworddiscovery_b200.engine_audio import pack_audio_pairs
+    rng = np.random.default_rng(0)
+    feats = [rng.standard_normal((int(rng.integers(1, 6)), 4)) for _ in range(11)]
+    audio = [rng.standard_normal((int(rng.integers(1, 9)), 3)) for _ in range(11)]
+    seen = []
+    for rank in range(2):
+        pk, aud = pack_audio_pairs(feats, audio, feat_dtype=np.float64, rank=rank, world=2)
+        assert np.array_equal(pk.phones, np.arange(pk.n_phones_total))
+        for s, ex in enumerate(pk.order):
+            np.testing.assert_array_equal(aud[pk.phone_off[s]:pk.phone_off[s + 1]], audio[int(ex)])
+            np.testing.assert_array_equal(pk.feats[pk.region_off[s]:pk.region_off[s + 1]], feats[int(ex)])
+        n = np.diff(pk.region_off)
+        assert np.all(np.diff(n) >= 0)
+        seen += [int(e) for e in pk.order]
+    assert sorted(seen) == list(range(11))
