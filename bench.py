@@ -34,6 +34,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 K_CONCEPTS, P_PHONES, D_FEAT = 65, 49, 512
+T_MEAN, T_STD = 50.0, 10.0
+# empirical region-count distribution of the Flickr30k captions (n mean 3.05, max 8)
+FLICKR_N_PMF = [0.12, 0.28, 0.27, 0.17, 0.09, 0.04, 0.02, 0.01]
+
+
+def apply_variant(variant):
+    """Workload shapes: coco5 / coco10 = C1/C5 (K=65, P=49, T~N(50,10)); flickr = C3
+    (K=100 concepts, P=69 phones, T~N(49,13), n ~ Flickr30k's empirical 1..8)."""
+    global K_CONCEPTS, P_PHONES, T_MEAN, T_STD
+    if variant == 'flickr':
+        K_CONCEPTS, P_PHONES, T_MEAN, T_STD = 100, 69, 49.0, 13.0
+    else:
+        K_CONCEPTS, P_PHONES, T_MEAN, T_STD = 65, 49, 50.0, 10.0
 METRIC = 'em_caption_pairs_per_sec'
 UNIT = 'pairs/s'
 
@@ -44,6 +57,9 @@ UNIT = 'pairs/s'
 def region_counts(n_pairs, variant, gen, torch, dev):
     if variant == 'coco5':
         return torch.full((n_pairs,), 5, dtype=torch.int64, device=dev)
+    if variant == 'flickr':
+        pmf = torch.tensor(FLICKR_N_PMF, dtype=torch.float64, device=dev)
+        return torch.multinomial(pmf, n_pairs, replacement=True, generator=gen) + 1
     return torch.randint(1, 11, (n_pairs,), generator=gen, device=dev)
 
 
@@ -53,7 +69,7 @@ def make_shard(torch, dev, n_pairs_global, rank, world, variant, seed=20261018):
     gen.manual_seed(seed)
     N = n_pairs_global
     # lengths for the WHOLE corpus (cheap), then the round-robin shard of the sorted order
-    T = torch.clamp(torch.round(50 + 10 * torch.randn(N, generator=gen, device=dev)), 15, 125).long()
+    T = torch.clamp(torch.round(T_MEAN + T_STD * torch.randn(N, generator=gen, device=dev)), 15, 125).long()
     n = region_counts(N, variant, gen, torch, dev)
     key = n * 1000 + T
     order = torch.argsort(key, stable=True)
@@ -109,8 +125,13 @@ def cpu_sample_numpy(n_pairs, variant, seed=20261018):
     pw /= pw.sum()
     feats, phones = [], []
     for _ in range(n_pairs):
-        T = int(np.clip(round(rng.normal(50, 10)), 15, 125))
-        n = 5 if variant == 'coco5' else int(rng.integers(1, 11))
+        T = int(np.clip(round(rng.normal(T_MEAN, T_STD)), 15, 125))
+        if variant == 'coco5':
+            n = 5
+        elif variant == 'flickr':
+            n = int(rng.choice(len(FLICKR_N_PMF), p=FLICKR_N_PMF)) + 1
+        else:
+            n = int(rng.integers(1, 11))
         v = centroids[rng.integers(0, K_CONCEPTS, n)] + rng.standard_normal((n, D_FEAT))
         feats.append(v.astype(np.float32).astype(np.float64))
         phones.append(rng.choice(P_PHONES, size=T, p=pw))
@@ -121,6 +142,7 @@ def _cpu_proc(idx, n_pairs, variant, n_rounds, barrier, out_q):
     """One CPU worker: builds ITS slice of the sample (untimed), then runs `n_rounds` E-steps of
     the NumPy oracle over it, each round released by the shared barrier."""
     from oracle import image_phone_hmm as orc
+    apply_variant(variant)
     feats, phones, W = cpu_sample_numpy(n_pairs, variant, seed=20261018 + 1000 + idx)
     params = orc.initial_params(feats, K_CONCEPTS, P_PHONES, 'linear', W=W, lr=0.1)
     params['toeplitz'] = variant != 'coco5'
@@ -186,11 +208,14 @@ def reference_arm(args):
 
 
 def workload_config(args, n_pairs):
-    return {'workload': 'image-phone HMM EM iteration, synthetic MSCOCO shape (%s): %d pairs, '
-                        'T~clip(N(50,10),15,125), K=%d concepts, P=%d phones, D=%d res34-like features'
-                        % (args.variant, n_pairs, K_CONCEPTS, P_PHONES, D_FEAT),
+    return {'workload': 'image-phone HMM EM iteration, synthetic %s shape (%s): %d pairs, '
+                        'T~clip(N(%g,%g),15,125), K=%d concepts, P=%d phones, D=%d res34-like features'
+                        % ('Flickr30k' if args.variant == 'flickr' else 'MSCOCO', args.variant, n_pairs, T_MEAN, T_STD,
+                           K_CONCEPTS, P_PHONES, D_FEAT),
             'pairs': n_pairs, 'variant': args.variant, 'class': 'ImagePhoneHMMWordDiscoverer',
-            'l2_policy': 'inputs (%.1f GB features) exceed the 126 MB L2' % (n_pairs * 5 * D_FEAT * 4 / 1e9),
+            'l2_policy': ('inputs (%.2f GB features) exceed the 126 MB L2' if n_pairs * 3 * D_FEAT * 4 > 126e6 else
+                          'inputs (%.2f GB features) fit in the 126 MB L2 and are NOT flushed (non-default size)')
+                         % (n_pairs * (3 if args.variant == 'flickr' else 5) * D_FEAT * 4 / 1e9),
             'parallelism': 'pairs sharded over %d GPU(s), one packed fp64 count all-reduce per iteration' % args.gpus}
 
 
@@ -461,12 +486,13 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--pairs', type=int, default=1000000)
-    ap.add_argument('--variant', default='coco5', choices=['coco5', 'coco10'])
+    ap.add_argument('--variant', default='coco5', choices=['coco5', 'coco10', 'flickr'])
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunks', type=int, default=0,
                     help='chunks of the streamed (e2e) iteration (0 = one per ~640 MB of shard, at most 16)')
     args = ap.parse_args()
+    apply_variant(args.variant)
     if args.impl == 'reference':
         reference_arm(args)
     else:

@@ -381,7 +381,8 @@ struct WarpPlan {
 #define MWD_WARP_COMBOS(X)                                                              \
   X(1, 2) X(1, 3) X(1, 4) X(2, 4) X(2, 5) X(2, 7) X(3, 5) X(3, 7) X(3, 10) X(4, 7) X(4, 9) \
   X(4, 13) X(5, 9) X(5, 11) X(6, 10) X(6, 13)                                             \
-  X(5, 17) X(7, 13) X(7, 17) X(8, 13) X(8, 17) X(9, 17) X(9, 22) X(10, 17) X(10, 22)
+  X(5, 17) X(7, 13) X(7, 17) X(8, 13) X(8, 17) X(9, 17) X(9, 22) X(10, 17) X(10, 22)                 \
+  X(6, 20) X(7, 25) X(8, 25)
 // register-block variant: compiled (and the default) for the MSCOCO concept count K = 65, n <= 8 (at
 // n = 5 it measured 55.1 vs 60.3 ms at 1M pairs); MWD_ESTEPW_RB=0 selects the shared-memory block
 // variant instead
