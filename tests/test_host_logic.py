@@ -140,3 +140,26 @@ def test_pack_audio_pairs_shards_cover_the_corpus():
         assert np.all(np.diff(n) >= 0)
         seen += [int(e) for e in pk.order]
     assert sorted(seen) == list(range(11))
+
+
+def test_segembed_batched_embedding_equals_per_segment_oracle():
+    """SegEmbedHMMWordDiscoverer.getSentEmbeds resamples all equal-length segments of an utterance in one
+    batched FFT call; the values must be those of the per-segment restatement (oracle/segembed_hmm.py,
+    reference hmm/audio_segembed_hmm_word_discoverer.py:114-155)."""
+    from oracle import segembed_hmm as sh
+    from multimodalworddiscovery_b200.hmm.audio_segembed_hmm_word_discoverer import (SegEmbedHMMWordDiscoverer,
+                                                                                      _clip_landmarks)
+    rng = np.random.default_rng(2)
+    m = SegEmbedHMMWordDiscoverer.__new__(SegEmbedHMMWordDiscoverer)
+    m.embedDim, m.frameDim, m.featDim = 120, 12, 13
+    x = rng.standard_normal((300, 13))
+    seg = [0, 7, 19, 26, 26 + 12, 60, 67, 100, 131, 138]          # repeated lengths 7 and 12
+    mine = m.getSentEmbeds(x, seg, frameDim=12)
+    ref = sh.sent_embeds(x, seg, 120, 12)
+    assert mine.shape == (len(seg) - 1, 120)
+    np.testing.assert_allclose(mine, ref, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(m.embed(x[7:19], frameDim=12), ref[1], rtol=1e-6, atol=1e-6)
+    assert m.getSentDurations(seg) == list(np.diff(seg))
+    # landmarks past maxLen collapse into one closing boundary (reference :68-76)
+    assert _clip_landmarks(np.array([0, 5, 9, 14, 30]), 10) == [0, 5, 9, 10]
+    assert _clip_landmarks(np.array([0, 5, 9]), 10) == [0, 5, 9]
