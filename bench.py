@@ -95,8 +95,10 @@ def make_shard(torch, dev, n_pairs_global, rank, world, variant, seed=20261018):
     pw = 1.0 / torch.arange(1, P_PHONES + 1, device=dev, dtype=torch.float64) ** 1.2
     phones = torch.multinomial(pw / pw.sum(), Tt, replacement=True, generator=gen2).to(torch.int32)
     W = 0.01 * torch.randn(K_CONCEPTS, D_FEAT + 1, generator=cgen, device=dev, dtype=torch.float64)
+    # gaussian class (configs[1]): visual anchors = the cluster centroids + noise
+    mus = centroids.double() + 0.5 * torch.randn(K_CONCEPTS, D_FEAT, generator=cgen, device=dev, dtype=torch.float64)
     return dict(region_off=region_off, phone_off=phone_off, feats=feats, phones=phones, lens=lens,
-                W=W, n_local=len(mine))
+                W=W, mus=mus, n_local=len(mine))
 
 
 def flops_per_pair(T_mean, n_mean, n3_mean):
@@ -212,7 +214,7 @@ def workload_config(args, n_pairs):
                         'T~clip(N(%g,%g),15,125), K=%d concepts, P=%d phones, D=%d res34-like features'
                         % ('Flickr30k' if args.variant == 'flickr' else 'MSCOCO', args.variant, n_pairs, T_MEAN, T_STD,
                            K_CONCEPTS, P_PHONES, D_FEAT),
-            'pairs': n_pairs, 'variant': args.variant, 'class': 'ImagePhoneHMMWordDiscoverer',
+            'pairs': n_pairs, 'variant': args.variant, 'class': 'ImagePhoneGaussianHMMWordDiscoverer' if args.model == 'gaussian' else 'ImagePhoneHMMWordDiscoverer',
             'l2_policy': ('inputs (%.2f GB features) exceed the 126 MB L2' if n_pairs * 3 * D_FEAT * 4 > 126e6 else
                           'inputs (%.2f GB features) fit in the 126 MB L2 and are NOT flushed (non-default size)')
                          % (n_pairs * (3 if args.variant == 'flickr' else 5) * D_FEAT * 4 / 1e9),
@@ -317,7 +319,9 @@ def gpu_arm(args):
                             host['phones'].numpy(), lens=sh['lens'], n_pairs_global=args.pairs)
     del sh['feats'], sh['phones']
     torch.cuda.empty_cache()
-    eng = IKEngine(pk, K_CONCEPTS, P_PHONES, gaussian=False, device=dev, keep_concept_counts_a=False)
+    gaussian = args.model == 'gaussian'
+    width = float(D_FEAT) if gaussian else 1.0       # RBF width of the order of |v - mu|^2 (unit-variance noise)
+    eng = IKEngine(pk, K_CONCEPTS, P_PHONES, gaussian=gaussian, device=dev, keep_concept_counts_a=False)
     if args.chunks <= 0:
         # enough chunks to overlap the PCIe copy with the kernels, not so many that a small corpus
         # drowns in launches (1 M pairs: 10.4 GB -> 16 chunks; MSCOCO-2k: 21 MB -> 1 chunk)
@@ -328,7 +332,7 @@ def gpu_arm(args):
     init = {m: np.ones(m) / m for m in pk.lens}
     trans = {m: np.ones((m, m)) / m for m in pk.lens}
     obs = np.ones((K_CONCEPTS, P_PHONES)) / P_PHONES
-    eng.set_params(init, trans, obs, sh['W'].cpu().numpy())
+    eng.set_params(init, trans, obs, (sh['mus'] if gaussian else sh['W']).cpu().numpy())
     snap = [t.clone() for t in (eng.init_t, eng.trans_t, eng.obsT, eng.post)]
     h_params = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in snap]
     h_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in snap]
@@ -341,14 +345,14 @@ def gpu_arm(args):
 
     def step_resident(timers=None):
         restore()
-        return eng.em_iteration(lr, mom, with_cA=False, timers=timers)
+        return eng.em_iteration(lr, mom, width, with_cA=False, timers=timers)
 
     def step_e2e():
         # host -> device: the shard (streamed in chunks that overlap the kernels) and the
         # parameters; device -> host: LL + updated tables
         for dst, src in zip((eng.init_t, eng.trans_t, eng.obsT, eng.post), h_params):
             dst.copy_(src, non_blocking=True)
-        ll = eng.em_iteration_streamed(host, lr, mom, n_chunks=args.chunks)
+        ll = eng.em_iteration_streamed(host, lr, mom, width, n_chunks=args.chunks)
         h_ll.copy_(ll.reshape(1), non_blocking=True)
         for dst, src in zip(h_out, (eng.init_t, eng.trans_t, eng.obsT, eng.post)):
             dst.copy_(src, non_blocking=True)
@@ -413,11 +417,11 @@ def gpu_arm(args):
     # shard under the current parameters (posterior GEMM + K6), alignments written to HBM
     restore()
     for _ in range(2):
-        eng.decode(want_probs=False)
+        eng.decode(floor_norm=gaussian, want_probs=False, width=width)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        eng.decode(want_probs=False)
+        eng.decode(floor_norm=gaussian, want_probs=False, width=width)
     e1.record()
     barrier()
     ms_align = max_over_ranks(e0.elapsed_time(e1)) / args.steps
@@ -487,6 +491,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--pairs', type=int, default=1000000)
     ap.add_argument('--variant', default='coco5', choices=['coco5', 'coco10', 'flickr'])
+    ap.add_argument('--model', default='linear', choices=['linear', 'gaussian'],
+                    help="image posterior: linear softmax (default, BASELINE configs[0]/[4]) or RBF (configs[1]); "
+                         "the CPU arm always times the linear class")
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunks', type=int, default=0,
