@@ -241,12 +241,15 @@ class IKEngine(object):
 
     def kernel_launches_per_iteration(self, n_chunks=None):
         """Kernels of libmwd_b200.so launched by one em_iteration / em_iteration_streamed."""
+        # posterior (RBF: + expansion kernel) | per bucket: recursion + count post-pass + concept chains |
+        # reduce_counts: 3 tables x 2 levels + 2 log-likelihood stages | gradient GEMM + its reduction |
+        # M-step: init/trans, obs, posterior parameter
         post = 2 if self.gaussian else 1
         if n_chunks is None:
             nb = int(np.count_nonzero(np.diff(self._bucket_lo) > 0))
-            return post + nb + nb + 5 + 2 + 3
-        per_chunk = sum(post + 2 * len(ch['bucket_n']) + 1 for ch in self.plan_chunks(n_chunks))
-        return per_chunk + 5 + 1 + 3
+            return post + 3 * nb + 8 + 2 + 3
+        per_chunk = sum(post + 3 * len(ch['bucket_n']) + 1 for ch in self.plan_chunks(n_chunks))
+        return per_chunk + 8 + 1 + 3
 
     def allreduce(self):
         """Sum [counts | grad] over ranks: all_gather + fixed-rank-order sum (bitwise reproducible)."""
