@@ -64,9 +64,12 @@ __device__ __forceinline__ double lse2(double a, double b) {
   return m + log(exp(a - m) + exp(b - m));
 }
 
-template <bool LOG>
+// NN > 0: the bucket's state count is a compile-time constant (state loops unroll, the per-lane
+// accumulator arrays shrink from kNMax to NN registers); NN == 0: generic (n > 8).
+template <bool LOG, int NN>
 __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
-  const int n = a.n, Vf = a.Vf;
+  constexpr int NU = NN > 0 ? NN : kNMax;
+  const int n = NN > 0 ? NN : a.n, Vf = a.Vf;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int j = lane;
   const bool on = j < n;
@@ -83,9 +86,9 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
 
   const double ident = LOG ? -INFINITY : 0.0;
   double init_acc = ident;
-  double tacc[kNMax];
+  double tacc[NU];
 #pragma unroll
-  for (int i = 0; i < kNMax; ++i) tacc[i] = ident;
+  for (int i = 0; i < NU; ++i) tacc[i] = ident;
 
   const int gw = blockIdx.x * a.warps_per_cta + wic;
   if (wic < a.warps_per_cta) {
@@ -115,14 +118,20 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
         const double* at = s_al + (size_t)t * n;
         if (LOG) {
           double m = -INFINITY;
-          for (int i = 0; i < n; ++i) m = fmax(m, s_A[i * n + (on ? j : 0)] + at[i]);
+#pragma unroll
+          for (int i = 0; i < NU; ++i)
+            if (NN > 0 || i < n) m = fmax(m, s_A[i * n + (on ? j : 0)] + at[i]);
           if (!(fabs(m) < INFINITY)) m = 0.0;
           double s = 0.0;
-          for (int i = 0; i < n; ++i) s += exp(s_A[i * n + (on ? j : 0)] + at[i] - m);
+#pragma unroll
+          for (int i = 0; i < NU; ++i)
+            if (NN > 0 || i < n) s += exp(s_A[i * n + (on ? j : 0)] + at[i] - m);
           al = log(s) + m + b;                                 // :165
         } else {
           double acc = 0.0;
-          for (int i = 0; i < n; ++i) acc = fma(s_A[i * n + (on ? j : 0)], at[i], acc);
+#pragma unroll
+          for (int i = 0; i < NU; ++i)
+            if (NN > 0 || i < n) acc = fma(s_A[i * n + (on ? j : 0)], at[i], acc);
           al = acc * b;                                        // :123
         }
         if (on) s_al[(size_t)(t + 1) * n + j] = al;
@@ -142,7 +151,9 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
             if (on) s_E[i * n + j] = s_al[(size_t)(T - 2) * n + i] + s_A[i * n + j] + bl;   // beta_{T-1} = 0
           __syncwarp();
           if (on) {
-            for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              if (NN == 0 && i >= n) break;
               const int dlt = j - i;
               double m = -INFINITY;
               for (int r = 0; r < n; ++r) {
@@ -174,10 +185,14 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
             if (on) s_x[j] = bb;
             __syncwarp();
             double m = -INFINITY;
-            for (int c = 0; c < n; ++c) m = fmax(m, s_A[(on ? j : 0) * n + c] + s_x[c]);
+#pragma unroll
+            for (int c = 0; c < NU; ++c)
+              if (NN > 0 || c < n) m = fmax(m, s_A[(on ? j : 0) * n + c] + s_x[c]);
             if (!(fabs(m) < INFINITY)) m = 0.0;
             double s = 0.0;
-            for (int c = 0; c < n; ++c) s += exp(s_A[(on ? j : 0) * n + c] + s_x[c] - m);
+#pragma unroll
+            for (int c = 0; c < NU; ++c)
+              if (NN > 0 || c < n) s += exp(s_A[(on ? j : 0) * n + c] + s_x[c] - m);
             beta = on ? log(s) + m : -INFINITY;                // :182
             __syncwarp();
           }
@@ -203,20 +218,22 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
             const double bb = beta * emis(t);
             // xi_{t-1}[i][j] = (alpha_{t-1}[i] * bb[j]) * A[i][j], normalised over (i, j)  (:161-162)
             const double* ap = s_al + (size_t)(t - 1) * n;
-            double xv[kNMax];
+            double xv[NU];
             double col = 0.0;
 #pragma unroll
-            for (int i = 0; i < kNMax; ++i) {
+            for (int i = 0; i < NU; ++i) {
               xv[i] = (i < n && on) ? (ap[i] * bb) * s_A[i * n + j] : 0.0;
               col += xv[i];
             }
             const double Z = warp_sum(col);
 #pragma unroll
-            for (int i = 0; i < kNMax; ++i) tacc[i] += xv[i] / Z;
+            for (int i = 0; i < NU; ++i) tacc[i] += xv[i] / Z;
             if (on) s_x[j] = bb;
             __syncwarp();
             double acc = 0.0;
-            for (int c = 0; c < n; ++c) acc = fma(s_A[(on ? j : 0) * n + c], s_x[c], acc);
+#pragma unroll
+            for (int c = 0; c < NU; ++c)
+              if (NN > 0 || c < n) acc = fma(s_A[(on ? j : 0) * n + c], s_x[c], acc);
             beta = on ? acc : 0.0;                             // :136
             __syncwarp();
           }
@@ -228,7 +245,7 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
       a.part_init[((size_t)gw * (kNMax + 1) + n) * kNMax + j] = init_acc;
       double* pt = a.part_trans + ((size_t)gw * (kNMax + 1) + n) * (kNMax * kNMax);
 #pragma unroll
-      for (int i = 0; i < kNMax; ++i)
+      for (int i = 0; i < NU; ++i)
         if (i < n) pt[i * n + j] = tacc[i];
     }
   }
@@ -626,13 +643,22 @@ extern "C" int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream) {
     a.lo = lo; a.hi = hi; a.n = n; a.Vf = p->n_src_types; a.Tmax = Tmax;
     a.warps_per_cta = wpc; a.total_warps = total;
     const size_t smem = fixed + (size_t)wpc * per_warp;
-    if (p->log_domain) {
-      MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_estep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      hmm_estep_kernel<true><<<grid, wpc * 32, smem, st>>>(a);
-    } else {
-      MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_estep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      hmm_estep_kernel<false><<<grid, wpc * 32, smem, st>>>(a);
+    auto launch = [&](auto kern) -> int {
+      MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, wpc * 32, smem, st>>>(a);
+      return 0;
+    };
+    int rc;
+    switch (n <= 8 ? n : 0) {
+#define MWD_HN(V)                                                                                     \
+  case V:                                                                                             \
+    rc = p->log_domain ? launch(hmm_estep_kernel<true, V>) : launch(hmm_estep_kernel<false, V>);      \
+    break;
+      MWD_HN(1) MWD_HN(2) MWD_HN(3) MWD_HN(4) MWD_HN(5) MWD_HN(6) MWD_HN(7) MWD_HN(8)
+#undef MWD_HN
+      default: rc = p->log_domain ? launch(hmm_estep_kernel<true, 0>) : launch(hmm_estep_kernel<false, 0>); break;
     }
+    if (rc) return rc;
     MWD_CHECK_LAUNCH();
   }
   return 0;
