@@ -12,6 +12,8 @@
 // observation counts go through a static postings index (slots sorted by (concept, phone) table
 // entry) and a segmented reduction -- no atomics anywhere.  The path is latency/HBM-bound
 // (~210 B and ~3.5 kFLOP per pair), so the design goal is many independent warps, not tensor cores.
+#include <stdlib.h>
+
 #include "mwd_common.cuh"
 
 namespace mwd {
@@ -248,6 +250,249 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
       for (int i = 0; i < NU; ++i)
         if (i < n) pt[i * n + j] = tacc[i];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Packed form of the discrete-observation E-step for n <= 8: a warp owns G = 32 / NN caption
+// pairs at once (lane = (sub-pair, state)), so all lanes carry a state instead of n of 32.
+// Every sub-pair has its own shared-memory slab (alpha / gamma block, beta exchange, log xi);
+// sums over the states of a pair are segment sums through a 32-double scratch row.  Sub-pairs
+// of a warp run in lock-step up to the longest caption of the group (pairs are sorted by T, so
+// the group is nearly uniform).  Same arithmetic per pair as hmm_estep_kernel.
+// ------------------------------------------------------------------------------------------
+template <bool LOG, int NN>
+__global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) {
+  constexpr int G = 32 / NN;
+  const int n = NN, Vf = a.Vf;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int sub = lane / NN, j = lane - sub * NN;
+  const bool lane_on = sub < G;
+  extern __shared__ double smem[];
+  const int slab = a.Tmax * NN + NN + (LOG ? NN * NN : 0);
+  const int per_warp = G * slab + 32 + G * (NN * NN + NN);
+  double* s_al = smem + (size_t)wic * per_warp + (lane_on ? sub : 0) * slab;   // [Tmax][NN]
+  double* s_x = s_al + (size_t)a.Tmax * NN;                                     // [NN]
+  double* s_E = s_x + NN;                                                       // [NN][NN] (LOG)
+  double* s_red = smem + (size_t)wic * per_warp + G * slab;                     // [32]
+  double* s_fin = s_red + 32;                                                   // [G][NN*NN + NN]
+  const int seg0 = (lane_on ? sub : 0) * NN;
+  auto seg_sum = [&](double v) -> double {
+    __syncwarp();
+    s_red[lane] = v;
+    __syncwarp();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) t += s_red[seg0 + i];
+    return t;
+  };
+  auto seg_lse = [&](double v) -> double {     // scipy.special.logsumexp over the states of the pair
+    __syncwarp();
+    s_red[lane] = v;
+    __syncwarp();
+    double m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) m = fmax(m, s_red[seg0 + i]);
+    if (!(fabs(m) < INFINITY)) m = 0.0;
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) t += exp(s_red[seg0 + i] - m);
+    return log(t) + m;
+  };
+  double acol[NN], arow[NN];                       // A[i][j], A[j][c]
+#pragma unroll
+  for (int i = 0; i < NN; ++i) {
+    acol[i] = a.trans[i * n + j];
+    arow[i] = a.trans[j * n + i];
+  }
+  const double pi_j = a.init[j];
+  const double ident = LOG ? -INFINITY : 0.0;
+  double init_acc = ident;
+  double tacc[NN];
+#pragma unroll
+  for (int i = 0; i < NN; ++i) tacc[i] = ident;
+
+  const int gw = blockIdx.x * a.warps_per_cta + wic;
+  for (int64_t base = a.lo + (int64_t)gw * G; base < a.hi; base += (int64_t)a.total_warps * G) {
+    const int64_t pair = base + sub;
+    const bool on = lane_on && pair < a.hi;
+    int f0 = 0, T = 0;
+    if (on) {
+      f0 = a.src_off[pair];
+      T = a.src_off[pair + 1] - f0;
+    }
+    const int Tw = __reduce_max_sync(0xffffffffu, T);
+    const int32_t* f = a.src + f0;
+    const int ej = on ? a.tgt[a.tgt_off[pair] + j] : 0;
+    const double* orow = a.obs + (size_t)ej * Vf;
+    const int64_t slot0 = on ? a.slot_off[pair] : 0;
+    auto emis = [&](int t) -> double {
+      double b = orow[f[t]];
+      return (b != b) ? 0.0 : b;           // absent pair: 0 in both classes (:122 / :161)
+    };
+    // ------------------------------------------------------------ forward
+    double al = ident;
+    if (on) {
+      const double b0 = orow[f[0]];
+      al = LOG ? pi_j + b0 : pi_j * ((b0 != b0) ? 0.0 : b0);   // :158 / :114-118
+      s_al[j] = al;
+    }
+    for (int t = 0; t + 1 < Tw; ++t) {
+      __syncwarp();
+      if (on && t + 1 < T) {
+        const double b = emis(t + 1);
+        const double* at = s_al + (size_t)t * NN;
+        if (LOG) {
+          double m = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < NN; ++i) m = fmax(m, acol[i] + at[i]);
+          if (!(fabs(m) < INFINITY)) m = 0.0;
+          double sm = 0.0;
+#pragma unroll
+          for (int i = 0; i < NN; ++i) sm += exp(acol[i] + at[i] - m);
+          al = log(sm) + m + b;                                // :165
+        } else {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < NN; ++i) acc = fma(acol[i], at[i], acc);
+          al = acc * b;                                        // :123
+        }
+        s_al[(size_t)(t + 1) * NN + j] = al;
+      }
+    }
+    __syncwarp();
+    {
+      const double last = on ? s_al[(size_t)(T - 1) * NN + j] : ident;
+      const double ll = LOG ? seg_lse(last) : log(seg_sum(last));   // :312 / :244-245
+      if (on && j == 0) a.pair_ll[pair] = ll;
+    }
+    // ------------------------------------------------------------ backward + counts
+    if (LOG) {
+      // transition counts from the LAST t only (:204-229)
+      if (on && T >= 2) {
+        const double bl = emis(T - 1);
+#pragma unroll
+        for (int i = 0; i < NN; ++i) s_E[i * NN + j] = s_al[(size_t)(T - 2) * NN + i] + acol[i] + bl;   // beta_{T-1} = 0
+      }
+      __syncwarp();
+      if (on && T >= 2) {
+#pragma unroll
+        for (int i = 0; i < NN; ++i) {
+          const int dlt = j - i;
+          double m = -INFINITY;
+#pragma unroll
+          for (int r = 0; r < NN; ++r) {
+            const int c = r + dlt;
+            if (c >= 0 && c < NN) m = fmax(m, s_E[r * NN + c]);
+          }
+          if (!(fabs(m) < INFINITY)) m = 0.0;
+          double sm = 0.0;
+#pragma unroll
+          for (int r = 0; r < NN; ++r) {
+            const int c = r + dlt;
+            if (c >= 0 && c < NN) sm += exp(s_E[r * NN + c] - m);
+          }
+          tacc[i] = lse2(tacc[i], log(sm) + m);
+        }
+      }
+      __syncwarp();
+      double beta = on ? 0.0 : -INFINITY;
+      double ic = -INFINITY, nrm = -INFINITY;
+      for (int t = Tw - 1; t >= 0; --t) {
+        const bool act = on && t < T;
+        const double v = act ? s_al[(size_t)t * NN + j] + beta : -INFINITY;
+        const double tot = seg_lse(v);
+        if (act) {
+          ic = lse2(ic, v);
+          nrm = lse2(nrm, tot);
+          s_al[(size_t)t * NN + j] = v;
+        }
+        if (t > 0) {
+          if (act) s_x[j] = beta + emis(t);
+          __syncwarp();
+          if (act) {
+            double m = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < NN; ++c) m = fmax(m, arow[c] + s_x[c]);
+            if (!(fabs(m) < INFINITY)) m = 0.0;
+            double sm = 0.0;
+#pragma unroll
+            for (int c = 0; c < NN; ++c) sm += exp(arow[c] + s_x[c] - m);
+            beta = log(sm) + m;                                // :182
+          }
+          __syncwarp();
+        }
+      }
+      if (on) init_acc = lse2(init_acc, ic);                   // :192-194
+      __syncwarp();
+      if (on)
+        for (int t = 0; t < T; ++t) a.post[slot0 + (int64_t)t * NN + j] = s_al[(size_t)t * NN + j] - nrm;   // :244-246
+      __syncwarp();
+    } else {
+      double beta = on ? 1.0 : 0.0;
+      for (int t = Tw - 1; t >= 0; --t) {
+        const bool act = on && t < T;
+        const double alv = act ? s_al[(size_t)t * NN + j] : 0.0;
+        const double g = alv * beta;
+        const double Gs = seg_sum(g);
+        if (act) {
+          const double gam = g / Gs;                           // :147-148, :193
+          init_acc += gam;
+          a.post[slot0 + (int64_t)t * NN + j] = gam;
+        }
+        if (t > 0) {
+          const double bb = act ? beta * emis(t) : 0.0;
+          // xi_{t-1}[i][j] = (alpha_{t-1}[i] * bb[j]) * A[i][j], normalised over (i, j)  (:161-162)
+          const double* ap = s_al + (size_t)(t - 1) * NN;
+          double xv[NN];
+          double col = 0.0;
+#pragma unroll
+          for (int i = 0; i < NN; ++i) {
+            xv[i] = act ? (ap[i] * bb) * acol[i] : 0.0;
+            col += xv[i];
+          }
+          const double Z = seg_sum(col);
+          if (act) {
+#pragma unroll
+            for (int i = 0; i < NN; ++i) tacc[i] += xv[i] / Z;
+            s_x[j] = bb;
+          }
+          __syncwarp();
+          if (act) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < NN; ++c) acc = fma(arow[c], s_x[c], acc);
+            beta = acc;                                        // :136
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  // combine the G sub-pair lanes of every state in fixed order, then the per-warp partial rows
+  __syncwarp();
+  if (lane_on) {
+    double* fin = s_fin + sub * (NN * NN + NN);
+    fin[NN * NN + j] = init_acc;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) fin[i * NN + j] = tacc[i];
+  }
+  __syncwarp();
+  if (lane < NN) {
+    double ia = ident;
+    double ta[NN];
+#pragma unroll
+    for (int i = 0; i < NN; ++i) ta[i] = ident;
+    for (int g = 0; g < G; ++g) {
+      const double* fin = s_fin + g * (NN * NN + NN);
+      ia = LOG ? lse2(ia, fin[NN * NN + lane]) : ia + fin[NN * NN + lane];
+#pragma unroll
+      for (int i = 0; i < NN; ++i) ta[i] = LOG ? lse2(ta[i], fin[i * NN + lane]) : ta[i] + fin[i * NN + lane];
+    }
+    a.part_init[((size_t)gw * (kNMax + 1) + n) * kNMax + lane] = ia;
+    double* pt = a.part_trans + ((size_t)gw * (kNMax + 1) + n) * (kNMax * kNMax);
+#pragma unroll
+    for (int i = 0; i < NN; ++i) pt[i * n + lane] = ta[i];
   }
 }
 
@@ -649,6 +894,37 @@ extern "C" int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream) {
       return 0;
     };
     int rc;
+    // packed kernel (several pairs per warp): discrete observations, no dense alpha / beta dump
+    const char* pk_env = getenv("MWD_HMM_PACKED");
+    if (n <= 8 && !p->emis && !p->alpha_out && !(pk_env && atoi(pk_env) == 0)) {
+      const int G = 32 / n;
+      const size_t pw_bytes = ((size_t)G * ((size_t)Tmax * n + n + (p->log_domain ? n * n : 0)) + 32 +
+                               (size_t)G * (n * n + n)) * sizeof(double);
+      int pwpc = 4;
+      while (pwpc > 1 && (pw_bytes * pwpc > 100 * 1024 || total % pwpc)) --pwpc;
+      if (pw_bytes * pwpc <= 220 * 1024 && total % pwpc == 0) {
+        HmmArgs b2 = a;
+        b2.warps_per_cta = pwpc;
+        const size_t psmem = pw_bytes * pwpc;
+        auto launch_p = [&](auto kern) -> int {
+          MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+          kern<<<total / pwpc, pwpc * 32, psmem, st>>>(b2);
+          return 0;
+        };
+        switch (n) {
+#define MWD_HP(V)                                                                                                   \
+  case V:                                                                                                           \
+    rc = p->log_domain ? launch_p(hmm_estep_packed_kernel<true, V>) : launch_p(hmm_estep_packed_kernel<false, V>);  \
+    break;
+          MWD_HP(1) MWD_HP(2) MWD_HP(3) MWD_HP(4) MWD_HP(5) MWD_HP(6) MWD_HP(7) MWD_HP(8)
+#undef MWD_HP
+          default: rc = 2; break;
+        }
+        if (rc) return rc;
+        MWD_CHECK_LAUNCH();
+        continue;
+      }
+    }
     switch (n <= 8 ? n : 0) {
 #define MWD_HN(V)                                                                                     \
   case V:                                                                                             \
