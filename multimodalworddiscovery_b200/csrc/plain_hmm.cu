@@ -327,13 +327,14 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
     const double* orow = a.obs + (size_t)ej * Vf;
     const int64_t slot0 = on ? a.slot_off[pair] : 0;
     auto emis = [&](int t) -> double {
+      if (LOG && a.emis) return a.emis[slot0 + (int64_t)t * NN + j];      // continuous (segment) model
       double b = orow[f[t]];
       return (b != b) ? 0.0 : b;           // absent pair: 0 in both classes (:122 / :161)
     };
     // ------------------------------------------------------------ forward
     double al = ident;
     if (on) {
-      const double b0 = orow[f[0]];
+      const double b0 = (LOG && a.emis) ? a.emis[slot0 + j] : orow[f[0]];
       al = LOG ? pi_j + b0 : pi_j * ((b0 != b0) ? 0.0 : b0);   // :158 / :114-118
       s_al[j] = al;
     }
@@ -894,9 +895,9 @@ extern "C" int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream) {
       return 0;
     };
     int rc;
-    // packed kernel (several pairs per warp): discrete observations, no dense alpha / beta dump
+    // packed kernel (several pairs per warp): every mode but the dense alpha / beta dump of forward()
     const char* pk_env = getenv("MWD_HMM_PACKED");
-    if (n <= 8 && !p->emis && !p->alpha_out && !(pk_env && atoi(pk_env) == 0)) {
+    if (n <= 8 && !p->alpha_out && !(pk_env && atoi(pk_env) == 0)) {
       const int G = 32 / n;
       const size_t pw_bytes = ((size_t)G * ((size_t)Tmax * n + n + (p->log_domain ? n * n : 0)) + 32 +
                                (size_t)G * (n * n + n)) * sizeof(double);
