@@ -162,10 +162,38 @@ __global__ void __launch_bounds__(kDecWarps * 32) ik_decode_kernel(const DecodeA
     // cluster (:586-597): scores[i][k] = pz[i][k] * prod_{t: align[t]==i} obs[k][x_t], in t order
     // time-major: step t multiplies the K scores of the aligned region by obs[:, x_t] (lanes over k);
     // every (i,k) product still runs in t order, each lane only ever touches its own columns
-    for (int t = 0; t < T; ++t) {
-      double* row = s_pz + s_ali[t] * K;
-      const double* orow = a.obsT + (size_t)s_x[t] * K;
-      for (int k = lane; k < K; k += 32) row[k] = __dmul_rn(row[k], __ldg(orow + k));
+    if constexpr (NN > 0 && NN <= 6) {
+      // scores of all NN regions in registers (4 column slots per lane cover K <= 128); the aligned
+      // region of a step is warp-uniform, so picking its register row is a uniform branch
+      double sc[NN][4];
+#pragma unroll
+      for (int i = 0; i < NN; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) sc[i][m] = (lane + 32 * m < K) ? s_pz[i * K + lane + 32 * m] : 0.0;
+      for (int t = 0; t < T; ++t) {
+        const int ai = s_ali[t];
+        const double* orow = a.obsT + (size_t)s_x[t] * K + lane;
+        double o[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) o[m] = (lane + 32 * m < K) ? __ldg(orow + 32 * m) : 0.0;
+#pragma unroll
+        for (int i = 0; i < NN; ++i)
+          if (ai == i) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sc[i][m] = __dmul_rn(sc[i][m], o[m]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < NN; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (lane + 32 * m < K) s_pz[i * K + lane + 32 * m] = sc[i][m];
+    } else {
+      for (int t = 0; t < T; ++t) {
+        double* row = s_pz + s_ali[t] * K;
+        const double* orow = a.obsT + (size_t)s_x[t] * K;
+        for (int k = lane; k < K; k += 32) row[k] = __dmul_rn(row[k], __ldg(orow + k));
+      }
     }
     __syncwarp();
     if (a.cluster_scores)
