@@ -243,12 +243,14 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
       }
     }
     // per-warp partial rows (one row per persistent warp and per n)
+    // (accumulated, not assigned: a state count may be split into several launches by caption length)
     if (on) {
-      a.part_init[((size_t)gw * (kNMax + 1) + n) * kNMax + j] = init_acc;
+      double* pi_out = a.part_init + ((size_t)gw * (kNMax + 1) + n) * kNMax + j;
+      *pi_out = LOG ? lse2(*pi_out, init_acc) : *pi_out + init_acc;
       double* pt = a.part_trans + ((size_t)gw * (kNMax + 1) + n) * (kNMax * kNMax);
 #pragma unroll
       for (int i = 0; i < NU; ++i)
-        if (i < n) pt[i * n + j] = tacc[i];
+        if (i < n) pt[i * n + j] = LOG ? lse2(pt[i * n + j], tacc[i]) : pt[i * n + j] + tacc[i];
     }
   }
 }
@@ -490,10 +492,11 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
 #pragma unroll
       for (int i = 0; i < NN; ++i) ta[i] = LOG ? lse2(ta[i], fin[i * NN + lane]) : ta[i] + fin[i * NN + lane];
     }
-    a.part_init[((size_t)gw * (kNMax + 1) + n) * kNMax + lane] = ia;
+    double* pi_out = a.part_init + ((size_t)gw * (kNMax + 1) + n) * kNMax + lane;
+    *pi_out = LOG ? lse2(*pi_out, ia) : *pi_out + ia;
     double* pt = a.part_trans + ((size_t)gw * (kNMax + 1) + n) * (kNMax * kNMax);
 #pragma unroll
-    for (int i = 0; i < NN; ++i) pt[i * n + lane] = ta[i];
+    for (int i = 0; i < NN; ++i) pt[i * n + lane] = LOG ? lse2(pt[i * n + lane], ta[i]) : pt[i * n + lane] + ta[i];
   }
 }
 
