@@ -14,11 +14,13 @@
 // (~210 B and ~3.5 kFLOP per pair), so the design goal is many independent warps, not tensor cores.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "mwd_common.cuh"
 
 namespace mwd {
 
-constexpr int kHmmWarpsPerSm = 16;
+constexpr int kHmmWarpsPerSm = 24;
 
 int hmm_warps_total() { return sm_count() * kHmmWarpsPerSm; }
 
@@ -258,26 +260,35 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
 // ------------------------------------------------------------------------------------------
 // Packed form of the discrete-observation E-step for n <= 8: a warp owns G = 32 / NN caption
 // pairs at once (lane = (sub-pair, state)), so all lanes carry a state instead of n of 32.
-// Every sub-pair has its own shared-memory slab (alpha / gamma block, beta exchange, log xi);
-// sums over the states of a pair are segment sums through a 32-double scratch row.  Sub-pairs
-// of a warp run in lock-step up to the longest caption of the group (pairs are sorted by T, so
-// the group is nearly uniform).  Same arithmetic per pair as hmm_estep_kernel.
+// The alpha lattice of the warp's G pairs lives in a per-warp GLOBAL scratch slab laid out
+// [t][lane] (one coalesced 256-byte row per step, L2-resident); shared memory only holds the
+// 32-double exchange rows through which the states of a pair see each other, so residency is
+// bounded by registers, not by the longest caption.  The backward sweep re-reads each lane's own
+// alpha two steps ahead of its use.  Sums over the states of a pair are segment sums through an
+// exchange row.  Sub-pairs of a warp run in lock-step up to the longest caption of the group
+// (pairs are sorted by T, so the group is nearly uniform).  Same arithmetic per pair as
+// hmm_estep_kernel.
 // ------------------------------------------------------------------------------------------
 template <bool LOG, int NN>
-__global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) {
+constexpr int hmm_packed_warp_doubles() {
+  return 4 * 32 + (LOG ? (32 / NN) * NN * NN : 0) + (32 / NN) * (NN * NN + NN);
+}
+
+template <bool LOG, int NN>
+__global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, double* scratch) {
   constexpr int G = 32 / NN;
   const int n = NN, Vf = a.Vf;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int sub = lane / NN, j = lane - sub * NN;
   const bool lane_on = sub < G;
   extern __shared__ double smem[];
-  const int slab = a.Tmax * NN + NN + (LOG ? NN * NN : 0);
-  const int per_warp = G * slab + 32 + G * (NN * NN + NN);
-  double* s_al = smem + (size_t)wic * per_warp + (lane_on ? sub : 0) * slab;   // [Tmax][NN]
-  double* s_x = s_al + (size_t)a.Tmax * NN;                                     // [NN]
-  double* s_E = s_x + NN;                                                       // [NN][NN] (LOG)
-  double* s_red = smem + (size_t)wic * per_warp + G * slab;                     // [32]
-  double* s_fin = s_red + 32;                                                   // [G][NN*NN + NN]
+  constexpr int per_warp = hmm_packed_warp_doubles<LOG, NN>();
+  double* s_w = smem + (size_t)wic * per_warp;
+  double* s_cur = s_w;                                        // [2][32] alpha exchange (double-buffered)
+  double* s_red = s_w + 64;                                   // [32] segment sums
+  double* s_xr = s_w + 96;                                    // [32] beta * b exchange
+  double* s_E = s_w + 128 + (lane_on ? sub : 0) * NN * NN;    // [NN][NN] per sub-pair (LOG)
+  double* s_fin = s_w + 128 + (LOG ? G * NN * NN : 0);        // [G][NN*NN + NN]
   const int seg0 = (lane_on ? sub : 0) * NN;
   auto seg_sum = [&](double v) -> double {
     __syncwarp();
@@ -315,6 +326,8 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
   for (int i = 0; i < NN; ++i) tacc[i] = ident;
 
   const int gw = blockIdx.x * a.warps_per_cta + wic;
+  double* g_row = scratch + (size_t)gw * a.Tmax * 32;        // [Tmax][32]
+  double* g_al = g_row + lane;
   for (int64_t base = a.lo + (int64_t)gw * G; base < a.hi; base += (int64_t)a.total_warps * G) {
     const int64_t pair = base + sub;
     const bool on = lane_on && pair < a.hi;
@@ -333,18 +346,23 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
       double b = orow[f[t]];
       return (b != b) ? 0.0 : b;           // absent pair: 0 in both classes (:122 / :161)
     };
+    auto own_alpha = [&](int t) -> double {    // this lane's alpha_t, 0 outside the pair's lattice
+      return (on && t >= 0 && t < T) ? g_al[(size_t)t * 32] : 0.0;
+    };
     // ------------------------------------------------------------ forward
     double al = ident;
     if (on) {
       const double b0 = (LOG && a.emis) ? a.emis[slot0 + j] : orow[f[0]];
       al = LOG ? pi_j + b0 : pi_j * ((b0 != b0) ? 0.0 : b0);   // :158 / :114-118
-      s_al[j] = al;
+      g_al[0] = al;
     }
+    __syncwarp();
+    s_cur[lane] = al;
     for (int t = 0; t + 1 < Tw; ++t) {
       __syncwarp();
       if (on && t + 1 < T) {
         const double b = emis(t + 1);
-        const double* at = s_al + (size_t)t * NN;
+        const double* at = s_cur + (t & 1) * 32 + seg0;
         if (LOG) {
           double m = -INFINITY;
 #pragma unroll
@@ -360,22 +378,24 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
           for (int i = 0; i < NN; ++i) acc = fma(acol[i], at[i], acc);
           al = acc * b;                                        // :123
         }
-        s_al[(size_t)(t + 1) * NN + j] = al;
+        g_al[(size_t)(t + 1) * 32] = al;
       }
+      s_cur[((t + 1) & 1) * 32 + lane] = al;      // past the pair's end: alpha_{T-1} stays
     }
-    __syncwarp();
     {
-      const double last = on ? s_al[(size_t)(T - 1) * NN + j] : ident;
+      const double last = on ? al : ident;                          // alpha_{T-1}
       const double ll = LOG ? seg_lse(last) : log(seg_sum(last));   // :312 / :244-245
       if (on && j == 0) a.pair_ll[pair] = ll;
     }
+    __syncwarp();        // the warp's alpha rows are visible to all its lanes from here
     // ------------------------------------------------------------ backward + counts
     if (LOG) {
       // transition counts from the LAST t only (:204-229)
       if (on && T >= 2) {
         const double bl = emis(T - 1);
+        const double* a2 = g_row + (size_t)(T - 2) * 32 + seg0;
 #pragma unroll
-        for (int i = 0; i < NN; ++i) s_E[i * NN + j] = s_al[(size_t)(T - 2) * NN + i] + acol[i] + bl;   // beta_{T-1} = 0
+        for (int i = 0; i < NN; ++i) s_E[i * NN + j] = a2[i] + acol[i] + bl;   // beta_{T-1} = 0
       }
       __syncwarp();
       if (on && T >= 2) {
@@ -401,41 +421,48 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
       __syncwarp();
       double beta = on ? 0.0 : -INFINITY;
       double ic = -INFINITY, nrm = -INFINITY;
+      double cur = own_alpha(Tw - 1), nx1 = own_alpha(Tw - 2), nx2 = own_alpha(Tw - 3);
       for (int t = Tw - 1; t >= 0; --t) {
         const bool act = on && t < T;
-        const double v = act ? s_al[(size_t)t * NN + j] + beta : -INFINITY;
+        const double v = act ? cur + beta : -INFINITY;
+        cur = nx1;
+        nx1 = nx2;
+        nx2 = own_alpha(t - 3);
         const double tot = seg_lse(v);
         if (act) {
           ic = lse2(ic, v);
           nrm = lse2(nrm, tot);
-          s_al[(size_t)t * NN + j] = v;
+          g_al[(size_t)t * 32] = v;
         }
         if (t > 0) {
-          if (act) s_x[j] = beta + emis(t);
+          s_xr[lane] = act ? beta + emis(t) : -INFINITY;
           __syncwarp();
           if (act) {
             double m = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < NN; ++c) m = fmax(m, arow[c] + s_x[c]);
+            for (int c = 0; c < NN; ++c) m = fmax(m, arow[c] + s_xr[seg0 + c]);
             if (!(fabs(m) < INFINITY)) m = 0.0;
             double sm = 0.0;
 #pragma unroll
-            for (int c = 0; c < NN; ++c) sm += exp(arow[c] + s_x[c] - m);
+            for (int c = 0; c < NN; ++c) sm += exp(arow[c] + s_xr[seg0 + c] - m);
             beta = log(sm) + m;                                // :182
           }
-          __syncwarp();
         }
       }
-      if (on) init_acc = lse2(init_acc, ic);                   // :192-194
-      __syncwarp();
-      if (on)
-        for (int t = 0; t < T; ++t) a.post[slot0 + (int64_t)t * NN + j] = s_al[(size_t)t * NN + j] - nrm;   // :244-246
+      if (on) {
+        init_acc = lse2(init_acc, ic);                         // :192-194
+        for (int t = 0; t < T; ++t) a.post[slot0 + (int64_t)t * NN + j] = g_al[(size_t)t * 32] - nrm;   // :244-246
+      }
       __syncwarp();
     } else {
       double beta = on ? 1.0 : 0.0;
+      double cur = own_alpha(Tw - 1), nx1 = own_alpha(Tw - 2), nx2 = own_alpha(Tw - 3);
       for (int t = Tw - 1; t >= 0; --t) {
         const bool act = on && t < T;
-        const double alv = act ? s_al[(size_t)t * NN + j] : 0.0;
+        const double alv = cur, prev = nx1;      // alpha_t[j], alpha_{t-1}[j] (0 outside the lattice)
+        cur = nx1;
+        nx1 = nx2;
+        nx2 = own_alpha(t - 3);
         const double g = alv * beta;
         const double Gs = seg_sum(g);
         if (act) {
@@ -445,8 +472,11 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
         }
         if (t > 0) {
           const double bb = act ? beta * emis(t) : 0.0;
+          s_cur[lane] = prev;
+          s_xr[lane] = bb;
+          __syncwarp();
           // xi_{t-1}[i][j] = (alpha_{t-1}[i] * bb[j]) * A[i][j], normalised over (i, j)  (:161-162)
-          const double* ap = s_al + (size_t)(t - 1) * NN;
+          const double* ap = s_cur + seg0;
           double xv[NN];
           double col = 0.0;
 #pragma unroll
@@ -454,22 +484,18 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
             xv[i] = act ? (ap[i] * bb) * acol[i] : 0.0;
             col += xv[i];
           }
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < NN; ++c) acc = fma(arow[c], s_xr[seg0 + c], acc);
           const double Z = seg_sum(col);
           if (act) {
 #pragma unroll
             for (int i = 0; i < NN; ++i) tacc[i] += xv[i] / Z;
-            s_x[j] = bb;
-          }
-          __syncwarp();
-          if (act) {
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < NN; ++c) acc = fma(arow[c], s_x[c], acc);
             beta = acc;                                        // :136
           }
-          __syncwarp();
         }
       }
+      __syncwarp();
     }
   }
   // combine the G sub-pair lanes of every state in fixed order, then the per-warp partial rows
@@ -501,25 +527,6 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a) 
 }
 
 // ---------------------------------------------------------------- reductions
-template <bool LOG>
-__global__ void hmm_reduce_rows_kernel(const double* __restrict__ part, int rows, int64_t elems,
-                                       double* __restrict__ out) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= elems) return;
-  if (LOG) {
-    double m = -INFINITY;
-    for (int r = 0; r < rows; ++r) m = fmax(m, part[(size_t)r * elems + e]);
-    if (m == -INFINITY) { out[e] = -INFINITY; return; }
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += exp(part[(size_t)r * elems + e] - m);
-    out[e] = log(s) + m;
-  } else {
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += part[(size_t)r * elems + e];
-    out[e] = s;
-  }
-}
-
 // one warp per (concept, phone) table entry, over its postings
 template <bool LOG>
 __global__ void hmm_postings_kernel(const double* __restrict__ post, const int64_t* __restrict__ idx,
@@ -548,6 +555,65 @@ __global__ void hmm_postings_kernel(const double* __restrict__ post, const int64
 
 // ---------------------------------------------------------------- M-step
 struct HmmLens { int lens[kNMax + 1]; int n; };
+
+// Reduction of the per-warp partial rows of the initial / transition counts, restricted to the state
+// counts the corpus actually has: one CTA per (state count m, table), thread = (row lane, element of
+// the m or m*m block); every row lane walks its rows in order, lanes combine in fixed order.
+// LOG: max over all rows first, then sum of exp(v - max) -- the two-pass logsumexp of the row loop
+// it replaces.  Everything outside the used blocks is the identity (written by hmm_fill_kernel).
+__global__ void hmm_fill_kernel(double* __restrict__ out, int64_t elems, double v) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < elems) out[e] = v;
+}
+
+constexpr int kReduceThreads = 1024;
+
+template <bool LOG>
+__global__ void __launch_bounds__(kReduceThreads) hmm_reduce_blocks_kernel(
+    const HmmLens la, const double* __restrict__ part_init, const double* __restrict__ part_trans, int rows,
+    double* __restrict__ out_init, double* __restrict__ out_trans) {
+  const int m = la.lens[blockIdx.x >> 1];
+  const bool is_trans = blockIdx.x & 1;
+  const int E = is_trans ? m * m : m;
+  const size_t stride = is_trans ? (size_t)(kNMax + 1) * kNMax * kNMax : (size_t)(kNMax + 1) * kNMax;
+  const size_t off = is_trans ? (size_t)m * kNMax * kNMax : (size_t)m * kNMax;
+  const double* src = (is_trans ? part_trans : part_init) + off;
+  double* dst = (is_trans ? out_trans : out_init) + off;
+  const int lanes = kReduceThreads / E;                  // row lanes per element (>= 4 for m <= 16)
+  const int e = threadIdx.x % E, rl = threadIdx.x / E;
+  const bool live = rl < lanes;
+  __shared__ double s_part[kReduceThreads];
+  __shared__ double s_max[kNMax * kNMax];
+  double mx = 0.0;
+  if (LOG) {
+    double v = -INFINITY;
+    if (live)
+      for (int r = rl; r < rows; r += lanes) v = fmax(v, src[(size_t)r * stride + e]);
+    s_part[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x < E) {
+      double t = -INFINITY;
+      for (int l = 0; l < lanes; ++l) t = fmax(t, s_part[l * E + threadIdx.x]);
+      s_max[threadIdx.x] = t;
+    }
+    __syncthreads();
+    mx = s_max[e];
+  }
+  double acc = 0.0;
+  if (live && !(LOG && mx == -INFINITY))
+    for (int r = rl; r < rows; r += lanes) {
+      const double v = src[(size_t)r * stride + e];
+      acc += LOG ? exp(v - mx) : v;
+    }
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < E) {
+    double t = 0.0;
+    for (int l = 0; l < lanes; ++l) t += s_part[l * E + threadIdx.x];
+    if (LOG) dst[threadIdx.x] = (s_max[threadIdx.x] == -INFINITY) ? -INFINITY : log(t) + s_max[threadIdx.x];
+    else dst[threadIdx.x] = t;
+  }
+}
 
 template <bool LOG>
 __global__ void hmm_mstep_init_trans_kernel(HmmLens la, const double* __restrict__ initC,
@@ -858,6 +924,38 @@ using namespace mwd;
 
 extern "C" int mwd_hmm_warps(void) { return hmm_warps_total(); }
 
+namespace {
+// The library's own stream-ordered pool (one per device) with an unbounded release threshold: a freed
+// scratch block stays in the pool, so the next call's allocation is a pointer bump, not a cudaMalloc.
+int scratch_pool(cudaMemPool_t* out) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  MWD_CHECK_CUDA(cudaGetDevice(&dev));
+  MWD_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    MWD_CHECK_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+    uint64_t keep = ~0ull;
+    MWD_CHECK_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  *out = pools[dev];
+  return 0;
+}
+
+struct ScratchGuard {   // stream-ordered free on every exit path
+  cudaStream_t st;
+  void* ptr = nullptr;
+  explicit ScratchGuard(cudaStream_t s) : st(s) {}
+  ~ScratchGuard() { if (ptr) cudaFreeAsync(ptr, st); }
+};
+}  // namespace
+
 extern "C" int64_t mwd_hmm_counts_len(int Vt, int Vf) {
   return (int64_t)Vt * Vf + (int64_t)(kNMax + 1) * kNMax + (int64_t)(kNMax + 1) * kNMax * kNMax + 1;
 }
@@ -865,6 +963,23 @@ extern "C" int64_t mwd_hmm_counts_len(int Vt, int Vf) {
 extern "C" int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream) {
   cudaStream_t st = as_stream(stream);
   const int total = hmm_warps_total();
+  const char* pk_env = getenv("MWD_HMM_PACKED");
+  // alpha scratch of the packed kernel: [warp][Tmax][32] doubles for the longest caption of any packed
+  // launch group, stream-ordered so the pool hands the same block back on every call
+  ScratchGuard guard(st);
+  double* scratch = nullptr;
+  {
+    int t_packed = 0;
+    for (int b = 0; b < p->n_buckets; ++b)
+      if (p->bucket_n[b] <= 8 && p->bucket_lo[b + 1] > p->bucket_lo[b] && p->bucket_tmax[b] > t_packed)
+        t_packed = p->bucket_tmax[b];
+    if (t_packed > 0 && !p->alpha_out && !(pk_env && atoi(pk_env) == 0)) {
+      cudaMemPool_t pool;
+      if (int rc = scratch_pool(&pool)) return rc;
+      MWD_CHECK_CUDA(cudaMallocFromPoolAsync(&guard.ptr, (size_t)total * t_packed * 32 * sizeof(double), pool, st));
+      scratch = static_cast<double*>(guard.ptr);
+    }
+  }
   for (int b = 0; b < p->n_buckets; ++b) {
     const int n = p->bucket_n[b];
     const int64_t lo = p->bucket_lo[b], hi = p->bucket_lo[b + 1];
@@ -899,35 +1014,39 @@ extern "C" int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream) {
     };
     int rc;
     // packed kernel (several pairs per warp): every mode but the dense alpha / beta dump of forward()
-    const char* pk_env = getenv("MWD_HMM_PACKED");
     if (n <= 8 && !p->alpha_out && !(pk_env && atoi(pk_env) == 0)) {
-      const int G = 32 / n;
-      const size_t pw_bytes = ((size_t)G * ((size_t)Tmax * n + n + (p->log_domain ? n * n : 0)) + 32 +
-                               (size_t)G * (n * n + n)) * sizeof(double);
-      int pwpc = 4;
-      while (pwpc > 1 && (pw_bytes * pwpc > 100 * 1024 || total % pwpc)) --pwpc;
-      if (pw_bytes * pwpc <= 220 * 1024 && total % pwpc == 0) {
-        HmmArgs b2 = a;
-        b2.warps_per_cta = pwpc;
-        const size_t psmem = pw_bytes * pwpc;
-        auto launch_p = [&](auto kern) -> int {
-          MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-          kern<<<total / pwpc, pwpc * 32, psmem, st>>>(b2);
-          return 0;
-        };
-        switch (n) {
-#define MWD_HP(V)                                                                                                   \
-  case V:                                                                                                           \
-    rc = p->log_domain ? launch_p(hmm_estep_packed_kernel<true, V>) : launch_p(hmm_estep_packed_kernel<false, V>);  \
+      const int pwpc = 4;
+      MWD_REQUIRE(total % pwpc == 0, "warp count %d not a multiple of %d", total, pwpc);
+      HmmArgs b2 = a;
+      b2.warps_per_cta = pwpc;
+      auto launch_p = [&](auto kern, int warp_doubles) -> int {
+        const size_t psmem = (size_t)pwpc * warp_doubles * sizeof(double);
+        MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        // persistent warps: never launch more CTAs than are resident at once (rows of the partial tables
+        // past the launched warps keep their identity fill)
+        int occ = 0;
+        MWD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pwpc * 32, psmem));
+        MWD_REQUIRE(occ >= 1, "packed recursion kernel does not fit on an SM");
+        int ctas = occ * sm_count();
+        if (ctas > total / pwpc) ctas = total / pwpc;
+        HmmArgs b3 = b2;
+        b3.total_warps = ctas * pwpc;
+        kern<<<ctas, pwpc * 32, psmem, st>>>(b3, scratch);
+        return 0;
+      };
+      switch (n) {
+#define MWD_HP(V)                                                                                              \
+  case V:                                                                                                      \
+    rc = p->log_domain ? launch_p(hmm_estep_packed_kernel<true, V>, hmm_packed_warp_doubles<true, V>())        \
+                       : launch_p(hmm_estep_packed_kernel<false, V>, hmm_packed_warp_doubles<false, V>());     \
     break;
-          MWD_HP(1) MWD_HP(2) MWD_HP(3) MWD_HP(4) MWD_HP(5) MWD_HP(6) MWD_HP(7) MWD_HP(8)
+        MWD_HP(1) MWD_HP(2) MWD_HP(3) MWD_HP(4) MWD_HP(5) MWD_HP(6) MWD_HP(7) MWD_HP(8)
 #undef MWD_HP
-          default: rc = 2; break;
-        }
-        if (rc) return rc;
-        MWD_CHECK_LAUNCH();
-        continue;
+        default: rc = 2; break;
       }
+      if (rc) return rc;
+      MWD_CHECK_LAUNCH();
+      continue;
     }
     switch (n <= 8 ? n : 0) {
 #define MWD_HN(V)                                                                                     \
@@ -952,14 +1071,29 @@ extern "C" int mwd_hmm_reduce(const mwd_hmm_problem* p, const int64_t* post_idx,
   const int64_t ie = (int64_t)(kNMax + 1) * kNMax;
   const int64_t te = (int64_t)(kNMax + 1) * kNMax * kNMax;
   const unsigned og = (unsigned)((oe + 7) / 8);
+  // state counts present in this shard (launch groups are sorted by state count)
+  HmmLens la;
+  la.n = 0;
+  for (int b = 0; b < p->n_buckets; ++b) {
+    const int m = p->bucket_n[b];
+    MWD_REQUIRE(m >= 1 && m <= kNMax, "bucket %d: %d states outside [1,%d]", b, m, kNMax);
+    bool seen = false;
+    for (int i = 0; i < la.n; ++i) seen = seen || la.lens[i] == m;
+    if (!seen) la.lens[la.n++] = m;
+  }
+  const unsigned fg = (unsigned)((ie + te + 255) / 256);
   if (p->log_domain) {
     if (!p->emis) hmm_postings_kernel<true><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
-    hmm_reduce_rows_kernel<true><<<(unsigned)((ie + 255) / 256), 256, 0, st>>>(p->part_init, rows, ie, counts + oe);
-    hmm_reduce_rows_kernel<true><<<(unsigned)((te + 255) / 256), 256, 0, st>>>(p->part_trans, rows, te, counts + oe + ie);
+    hmm_fill_kernel<<<fg, 256, 0, st>>>(counts + oe, ie + te, -INFINITY);
+    if (la.n)
+      hmm_reduce_blocks_kernel<true><<<2 * la.n, kReduceThreads, 0, st>>>(la, p->part_init, p->part_trans, rows,
+                                                                        counts + oe, counts + oe + ie);
   } else {
     hmm_postings_kernel<false><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
-    hmm_reduce_rows_kernel<false><<<(unsigned)((ie + 255) / 256), 256, 0, st>>>(p->part_init, rows, ie, counts + oe);
-    hmm_reduce_rows_kernel<false><<<(unsigned)((te + 255) / 256), 256, 0, st>>>(p->part_trans, rows, te, counts + oe + ie);
+    hmm_fill_kernel<<<fg, 256, 0, st>>>(counts + oe, ie + te, 0.0);
+    if (la.n)
+      hmm_reduce_blocks_kernel<false><<<2 * la.n, kReduceThreads, 0, st>>>(la, p->part_init, p->part_trans, rows,
+                                                                         counts + oe, counts + oe + ie);
   }
   MWD_CHECK_LAUNCH();
   // log-likelihood sum; stage-1 partials parked in the (already consumed) head of part_trans
