@@ -257,6 +257,16 @@ __global__ void __launch_bounds__(256) hmm_estep_kernel(const HmmArgs a) {
   }
 }
 
+// exact logsumexp_i(w[i * stride] + x[i]): the out-of-line fallback of the packed kernel's weighted form
+__device__ __noinline__ double lse_exact(const double* w, int stride, const double* x, int nn) {
+  double m = -INFINITY;
+  for (int i = 0; i < nn; ++i) m = fmax(m, w[i * stride] + x[i]);
+  if (!(fabs(m) < INFINITY)) m = 0.0;
+  double sm = 0.0;
+  for (int i = 0; i < nn; ++i) sm += exp(w[i * stride] + x[i] - m);
+  return log(sm) + m;
+}
+
 // ------------------------------------------------------------------------------------------
 // Packed form of the discrete-observation E-step for n <= 8: a warp owns G = 32 / NN caption
 // pairs at once (lane = (sub-pair, state)), so all lanes carry a state instead of n of 32.
@@ -299,7 +309,9 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
     for (int i = 0; i < NN; ++i) t += s_red[seg0 + i];
     return t;
   };
-  auto seg_lse = [&](double v) -> double {     // scipy.special.logsumexp over the states of the pair
+  // scipy.special.logsumexp over the states of the pair (max, sum of exp(v - max) in state order, log);
+  // every lane exponentiates its OWN term once and the terms are summed through an exchange row
+  auto seg_lse = [&](double v) -> double {
     __syncwarp();
     s_red[lane] = v;
     __syncwarp();
@@ -307,17 +319,40 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
 #pragma unroll
     for (int i = 0; i < NN; ++i) m = fmax(m, s_red[seg0 + i]);
     if (!(fabs(m) < INFINITY)) m = 0.0;
+    s_cur[lane] = exp(v - m);
+    __syncwarp();
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < NN; ++i) t += exp(s_red[seg0 + i] - m);
+    for (int i = 0; i < NN; ++i) t += s_cur[seg0 + i];
     return log(t) + m;
   };
-  double acol[NN], arow[NN];                       // A[i][j], A[j][c]
+  // logsumexp_i(w_log[i] + x[i]) for a fixed weight vector (a column / row of log A) and the pair's state
+  // vector x (own entry x_own, all entries in row[seg0..]): with mg = max_i x[i] the sum is
+  // sum_i exp(w_log[i]) * exp(x[i] - mg) -- ONE exp per lane (its own entry, shared through `xch`) instead
+  // of one per (i, j).  If the weighted sum underflows (the dominant x[i] carries a zero / tiny weight)
+  // the exact per-term form is evaluated instead.  `w_log(i)` reads log A from global memory.
+  auto lse_weighted = [&](const double (&w_lin)[NN], const double* w_log, int w_stride, const double* row,
+                          double x_own, double* xch, bool act) -> double {
+    double mg = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) mg = fmax(mg, row[seg0 + i]);
+    if (!(fabs(mg) < INFINITY)) mg = 0.0;
+    xch[lane] = act ? exp(x_own - mg) : 0.0;
+    __syncwarp();
+    double S = 0.0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) S = fma(w_lin[i], xch[seg0 + i], S);
+    if (S > 1e-280 || !act) return log(S) + mg;
+    return lse_exact(w_log, w_stride, row + seg0, NN);
+  };
+  double acol[NN], arow[NN];                       // A[i][j], A[j][c]  (LOG: exp of the log table)
 #pragma unroll
   for (int i = 0; i < NN; ++i) {
-    acol[i] = a.trans[i * n + j];
-    arow[i] = a.trans[j * n + i];
+    acol[i] = LOG ? exp(a.trans[i * n + j]) : a.trans[i * n + j];
+    arow[i] = LOG ? exp(a.trans[j * n + i]) : a.trans[j * n + i];
   }
+  const double* lcol = a.trans + j;        // log A[i][j] = lcol[i * n]   (LOG, rare paths)
+  const double* lrow = a.trans + j * n;    // log A[j][c] = lrow[c]
   const double pi_j = a.init[j];
   const double ident = LOG ? -INFINITY : 0.0;
   double init_acc = ident;
@@ -358,28 +393,24 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
     }
     __syncwarp();
     s_cur[lane] = al;
+    // emissions are fetched one step ahead of their use: the gather never sits on the recursion's chain
+    double b_next = (on && 1 < T) ? emis(1) : 0.0;
     for (int t = 0; t + 1 < Tw; ++t) {
       __syncwarp();
-      if (on && t + 1 < T) {
-        const double b = emis(t + 1);
+      const double b = b_next;
+      b_next = (on && t + 2 < T) ? emis(t + 2) : 0.0;
+      const bool step = on && t + 1 < T;
+      if (LOG) {
+        const double nv = lse_weighted(acol, lcol, n, s_cur + (t & 1) * 32, al, s_xr, step) + b;   // :165
+        if (step) al = nv;
+      } else if (step) {
         const double* at = s_cur + (t & 1) * 32 + seg0;
-        if (LOG) {
-          double m = -INFINITY;
+        double acc = 0.0;
 #pragma unroll
-          for (int i = 0; i < NN; ++i) m = fmax(m, acol[i] + at[i]);
-          if (!(fabs(m) < INFINITY)) m = 0.0;
-          double sm = 0.0;
-#pragma unroll
-          for (int i = 0; i < NN; ++i) sm += exp(acol[i] + at[i] - m);
-          al = log(sm) + m + b;                                // :165
-        } else {
-          double acc = 0.0;
-#pragma unroll
-          for (int i = 0; i < NN; ++i) acc = fma(acol[i], at[i], acc);
-          al = acc * b;                                        // :123
-        }
-        g_al[(size_t)(t + 1) * 32] = al;
+        for (int i = 0; i < NN; ++i) acc = fma(acol[i], at[i], acc);
+        al = acc * b;                                          // :123
       }
+      if (step) g_al[(size_t)(t + 1) * 32] = al;
       s_cur[((t + 1) & 1) * 32 + lane] = al;      // past the pair's end: alpha_{T-1} stays
     }
     {
@@ -395,7 +426,7 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
         const double bl = emis(T - 1);
         const double* a2 = g_row + (size_t)(T - 2) * 32 + seg0;
 #pragma unroll
-        for (int i = 0; i < NN; ++i) s_E[i * NN + j] = a2[i] + acol[i] + bl;   // beta_{T-1} = 0
+        for (int i = 0; i < NN; ++i) s_E[i * NN + j] = a2[i] + lcol[i * n] + bl;   // beta_{T-1} = 0
       }
       __syncwarp();
       if (on && T >= 2) {
@@ -420,35 +451,45 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
       }
       __syncwarp();
       double beta = on ? 0.0 : -INFINITY;
-      double ic = -INFINITY, nrm = -INFINITY;
+      // running logsumexp over t of v (ic) and of tot (nrm) as (max, scaled sum): one exp per step each
+      double ic_m = -INFINITY, ic_s = 0.0, nrm_m = -INFINITY, nrm_s = 0.0;
+      auto lse_push = [](double& m, double& sacc, double v) {
+        if (v == -INFINITY) return;
+        const double d = v - m;
+        const double e = exp(-fabs(d));
+        if (d > 0.0) {
+          sacc = sacc * e + 1.0;
+          m = v;
+        } else {
+          sacc += e;
+        }
+      };
       double cur = own_alpha(Tw - 1), nx1 = own_alpha(Tw - 2), nx2 = own_alpha(Tw - 3);
+      double e_next = (on && Tw - 1 < T && Tw - 1 > 0) ? emis(Tw - 1) : 0.0;
       for (int t = Tw - 1; t >= 0; --t) {
         const bool act = on && t < T;
         const double v = act ? cur + beta : -INFINITY;
         cur = nx1;
         nx1 = nx2;
         nx2 = own_alpha(t - 3);
+        const double e_t = e_next;                       // emission of step t, fetched one step earlier
+        e_next = (on && t - 1 < T && t - 1 > 0) ? emis(t - 1) : 0.0;
         const double tot = seg_lse(v);
         if (act) {
-          ic = lse2(ic, v);
-          nrm = lse2(nrm, tot);
+          lse_push(ic_m, ic_s, v);
+          lse_push(nrm_m, nrm_s, tot);
           g_al[(size_t)t * 32] = v;
         }
         if (t > 0) {
-          s_xr[lane] = act ? beta + emis(t) : -INFINITY;
+          const double x = act ? beta + e_t : -INFINITY;
+          s_xr[lane] = x;
           __syncwarp();
-          if (act) {
-            double m = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < NN; ++c) m = fmax(m, arow[c] + s_xr[seg0 + c]);
-            if (!(fabs(m) < INFINITY)) m = 0.0;
-            double sm = 0.0;
-#pragma unroll
-            for (int c = 0; c < NN; ++c) sm += exp(arow[c] + s_xr[seg0 + c] - m);
-            beta = log(sm) + m;                                // :182
-          }
+          const double nb = lse_weighted(arow, lrow, 1, s_xr, x, s_red, act);   // :182
+          if (act) beta = nb;
         }
       }
+      const double ic = ic_s > 0.0 ? log(ic_s) + ic_m : -INFINITY;
+      const double nrm = nrm_s > 0.0 ? log(nrm_s) + nrm_m : -INFINITY;
       if (on) {
         init_acc = lse2(init_acc, ic);                         // :192-194
         for (int t = 0; t < T; ++t) a.post[slot0 + (int64_t)t * NN + j] = g_al[(size_t)t * 32] - nrm;   // :244-246
@@ -457,12 +498,15 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
     } else {
       double beta = on ? 1.0 : 0.0;
       double cur = own_alpha(Tw - 1), nx1 = own_alpha(Tw - 2), nx2 = own_alpha(Tw - 3);
+      double e_next = (on && Tw - 1 < T && Tw - 1 > 0) ? emis(Tw - 1) : 0.0;
       for (int t = Tw - 1; t >= 0; --t) {
         const bool act = on && t < T;
         const double alv = cur, prev = nx1;      // alpha_t[j], alpha_{t-1}[j] (0 outside the lattice)
         cur = nx1;
         nx1 = nx2;
         nx2 = own_alpha(t - 3);
+        const double e_t = e_next;                       // emission of step t, fetched one step earlier
+        e_next = (on && t - 1 < T && t - 1 > 0) ? emis(t - 1) : 0.0;
         const double g = alv * beta;
         const double Gs = seg_sum(g);
         if (act) {
@@ -471,7 +515,7 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
           a.post[slot0 + (int64_t)t * NN + j] = gam;
         }
         if (t > 0) {
-          const double bb = act ? beta * emis(t) : 0.0;
+          const double bb = act ? beta * e_t : 0.0;
           s_cur[lane] = prev;
           s_xr[lane] = bb;
           __syncwarp();

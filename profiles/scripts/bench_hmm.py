@@ -22,6 +22,7 @@ def main():
     ap.add_argument('--pairs', type=int, default=200000)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=2)
+    ap.add_argument('--domain', choices=('both', 'prob', 'log'), default='both')
     args = ap.parse_args()
     import torch
     from multimodalworddiscovery_b200.engine_hmm import PackedSentences, PlainHMMEngine
@@ -33,7 +34,7 @@ def main():
     tgt = [rng.integers(0, Vt, n) for n in ns]
     src = [rng.integers(0, Vf, T) for T in Ts]
     pk = PackedSentences(tgt, src, Vf)
-    for log_domain in (False, True):
+    for log_domain in {'both': (False, True), 'prob': (False,), 'log': (True,)}[args.domain]:
         eng = PlainHMMEngine(pk, Vt, Vf, log_domain)
         lens = pk.lens
         if log_domain:
