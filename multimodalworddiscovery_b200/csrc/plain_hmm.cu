@@ -775,6 +775,7 @@ struct HmmAlignArgs {
   const double* emis;
   const int64_t* slot_off;
   int64_t n_pairs;
+  int64_t lo, hi;          // pair range of this launch
   int Vf, Tmax, warps_per_cta;
   double unk;
 };
@@ -786,8 +787,8 @@ __device__ __forceinline__ bool np_greater_h(double cand, double best) {
 template <bool LOG>
 __global__ void __launch_bounds__(256) hmm_align_kernel(const HmmAlignArgs a) {
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int64_t pair = (int64_t)blockIdx.x * a.warps_per_cta + wic;
-  if (wic >= a.warps_per_cta || pair >= a.n_pairs) return;
+  const int64_t pair = a.lo + (int64_t)blockIdx.x * a.warps_per_cta + wic;
+  if (wic >= a.warps_per_cta || pair >= a.hi) return;
   extern __shared__ double smem[];
   const size_t per_warp = 2 * kNMax * sizeof(double) + (size_t)a.Tmax * kNMax;
   unsigned char* base = reinterpret_cast<unsigned char*>(smem) + (size_t)wic * ((per_warp + 7) / 8 * 8);
@@ -849,6 +850,103 @@ __global__ void __launch_bounds__(256) hmm_align_kernel(const HmmAlignArgs a) {
     a.alignment[f0 + T - 1] = cur;
     for (int t = T - 1; t > 0; --t) {
       cur = s_bp[t * kNMax + cur];
+      a.alignment[f0 + t - 1] = cur;
+    }
+  }
+}
+
+// Packed Viterbi for n <= 8: a warp decodes G = 32 / NN pairs at once (lane = (sub-pair, state)), scores
+// exchanged through a double-buffered 32-double row, back-pointers one byte per (t, lane); the G
+// back-traces run in parallel, one lane per pair.  Same products / comparisons per pair, in the same
+// order, as hmm_align_kernel (first index wins ties, NaN handling of np.argmax).
+template <bool LOG, int NN>
+__global__ void __launch_bounds__(256) hmm_align_packed_kernel(const HmmAlignArgs a) {
+  constexpr int G = 32 / NN;
+  const int n = NN;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int sub = lane / NN, j = lane - sub * NN;
+  const bool lane_on = sub < G;
+  const int seg0 = (lane_on ? sub : 0) * NN;
+  extern __shared__ double smem[];
+  const size_t per_warp = 2 * 32 * sizeof(double) + (size_t)a.Tmax * 32;
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(smem) + (size_t)wic * per_warp;
+  double* s_sc = reinterpret_cast<double*>(wbase);           // [2][32]
+  unsigned char* s_bp = wbase + 2 * 32 * sizeof(double);     // [Tmax][32]
+  const int64_t pair = a.lo + ((int64_t)blockIdx.x * a.warps_per_cta + wic) * G + sub;
+  const bool on = lane_on && pair < a.hi;
+  int e0 = 0, f0 = 0, T = 0;
+  if (on) {
+    e0 = a.tgt_off[pair];
+    f0 = a.src_off[pair];
+    T = a.src_off[pair + 1] - f0;
+  }
+  const int Tw = __reduce_max_sync(0xffffffffu, T);
+  if (Tw == 0) return;
+  const int32_t* f = a.src + f0;
+  const double* A = a.trans + (size_t)n * MWD_TRANS_STRIDE;
+  double acol[NN];
+#pragma unroll
+  for (int i = 0; i < NN; ++i) acol[i] = A[i * n + j];
+  const double* orow = a.obs + (size_t)(on ? a.tgt[e0 + j] : 0) * a.Vf;
+  double* ap = (a.align_probs && on) ? a.align_probs + a.ap_off[pair] : nullptr;
+  const int64_t slot0 = (a.emis && on) ? a.slot_off[pair] : 0;
+  auto emis = [&](int t) -> double {
+    double b = a.emis ? a.emis[slot0 + (int64_t)t * n + j] : orow[f[t]];
+    return (b != b) ? a.unk : b;                              // :311 / :407
+  };
+  double sc = 0.0;
+  if (on) {
+    const double b0 = a.emis ? a.emis[slot0 + j] : orow[f[0]];
+    const double pj = a.init[(size_t)n * MWD_INIT_STRIDE + j];
+    sc = LOG ? pj + b0 : pj * b0;                             // :307 / :402
+  }
+  s_sc[lane] = sc;
+  double b_next = (on && 1 < T) ? emis(1) : 0.0;
+  for (int t = 1; t < Tw; ++t) {
+    __syncwarp();
+    const double* prev = s_sc + ((t - 1) & 1) * 32 + seg0;
+    const bool act = on && t < T;
+    const double b = b_next;
+    b_next = (on && t + 1 < T) ? emis(t + 1) : 0.0;
+    if (act) {
+      double best = LOG ? __dadd_rn(__dadd_rn(prev[0], acol[0]), b) : __dmul_rn(__dmul_rn(prev[0], acol[0]), b);
+      int arg = 0;
+#pragma unroll
+      for (int i = 1; i < NN; ++i) {
+        const double cand = LOG ? __dadd_rn(__dadd_rn(prev[i], acol[i]), b)
+                                : __dmul_rn(__dmul_rn(prev[i], acol[i]), b);
+        if (np_greater_h(cand, best)) { best = cand; arg = i; }
+      }
+      s_bp[t * 32 + lane] = (unsigned char)arg;
+      sc = best;
+    }
+    double* next = s_sc + (t & 1) * 32;
+    next[lane] = sc;                  // finished pairs keep re-posting their final scores
+    if (a.align_probs) {              // warp-uniform
+      if (LOG) {
+        if (act) ap[(size_t)(t - 1) * n + j] = sc;            // :414
+      } else {
+        __syncwarp();
+        if (act) {
+          double tot = 0.0;
+#pragma unroll
+          for (int i = 0; i < NN; ++i) tot += next[seg0 + i];
+          ap[(size_t)(t - 1) * n + j] = sc / tot;             // :316
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (on && j == 0) {
+    const double* fin = s_sc + ((Tw - 1) & 1) * 32 + seg0;
+    double best = fin[0];
+    int cur = 0;
+#pragma unroll
+    for (int i = 1; i < NN; ++i)
+      if (np_greater_h(fin[i], best)) { best = fin[i]; cur = i; }
+    a.alignment[f0 + T - 1] = cur;
+    for (int t = T - 1; t > 0; --t) {
+      cur = s_bp[t * 32 + seg0 + cur];
       a.alignment[f0 + t - 1] = cur;
     }
   }
@@ -1178,29 +1276,72 @@ extern "C" int mwd_hmm_align(const mwd_hmm_problem* p, double unk_prob, int32_t*
   cudaStream_t st = as_stream(stream);
   if (p->n_pairs <= 0) return 0;
   MWD_REQUIRE(align_probs == nullptr || ap_off != nullptr, "align_probs needs ap_off");
+  MWD_REQUIRE(p->n_buckets > 0 && p->bucket_lo && p->bucket_n && p->bucket_tmax, "align needs the launch groups");
   HmmAlignArgs a;
   a.tgt_off = p->tgt_off; a.tgt = p->tgt; a.src_off = p->src_off; a.src = p->src;
   a.init = p->init; a.trans = p->trans; a.obs = p->obs;
   a.alignment = alignment; a.align_probs = align_probs; a.ap_off = ap_off;
   a.emis = p->emis; a.slot_off = p->slot_off;
   a.n_pairs = p->n_pairs; a.Vf = p->n_src_types; a.Tmax = p->t_max; a.unk = unk_prob;
-  size_t per_warp = 2 * kNMax * sizeof(double) + (size_t)a.Tmax * kNMax;
-  per_warp = (per_warp + 7) / 8 * 8;
-  int wpc = (int)((220 * 1024) / per_warp);
-  if (wpc > 8) wpc = 8;
-  MWD_REQUIRE(wpc >= 1, "caption of %d tokens does not fit in shared memory", a.Tmax);
-  a.warps_per_cta = wpc;
-  const size_t smem = per_warp * wpc;
-  const int64_t grid = (p->n_pairs + wpc - 1) / wpc;
-  MWD_REQUIRE(grid <= 0x7fffffff, "too many pairs for one launch");
-  if (p->log_domain) {
-    MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hmm_align_kernel<true><<<(unsigned)grid, wpc * 32, smem, st>>>(a);
-  } else {
-    MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hmm_align_kernel<false><<<(unsigned)grid, wpc * 32, smem, st>>>(a);
+  const char* pk_env = getenv("MWD_HMM_PACKED");
+  const bool packed_ok = !(pk_env && atoi(pk_env) == 0);
+  for (int b = 0; b < p->n_buckets; ++b) {
+    const int n = p->bucket_n[b];
+    a.lo = p->bucket_lo[b];
+    a.hi = p->bucket_lo[b + 1];
+    if (a.hi <= a.lo) continue;
+    MWD_REQUIRE(n >= 1 && n <= kNMax, "bucket %d: %d states outside [1,%d]", b, n, kNMax);
+    a.Tmax = p->bucket_tmax[b];
+    const int64_t npairs = a.hi - a.lo;
+    if (n <= 8 && packed_ok) {
+      // several pairs per warp; back-pointers are one byte per (t, lane)
+      const int G = 32 / n;
+      const size_t per_warp = 2 * 32 * sizeof(double) + (size_t)a.Tmax * 32;
+      int wpc = (int)((220 * 1024) / per_warp);
+      if (wpc > 8) wpc = 8;
+      MWD_REQUIRE(wpc >= 1, "caption of %d tokens does not fit in shared memory", a.Tmax);
+      a.warps_per_cta = wpc;
+      const size_t smem = per_warp * wpc;
+      const int64_t groups = (npairs + G - 1) / G;
+      const int64_t grid = (groups + wpc - 1) / wpc;
+      MWD_REQUIRE(grid <= 0x7fffffff, "too many pairs for one launch");
+      auto launch_p = [&](auto kern) -> int {
+        MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, wpc * 32, smem, st>>>(a);
+        return 0;
+      };
+      int rc;
+      switch (n) {
+#define MWD_AP(V)                                                                                                 \
+  case V:                                                                                                         \
+    rc = p->log_domain ? launch_p(hmm_align_packed_kernel<true, V>) : launch_p(hmm_align_packed_kernel<false, V>); \
+    break;
+        MWD_AP(1) MWD_AP(2) MWD_AP(3) MWD_AP(4) MWD_AP(5) MWD_AP(6) MWD_AP(7) MWD_AP(8)
+#undef MWD_AP
+        default: rc = 2; break;
+      }
+      if (rc) return rc;
+      MWD_CHECK_LAUNCH();
+      continue;
+    }
+    size_t per_warp = 2 * kNMax * sizeof(double) + (size_t)a.Tmax * kNMax;
+    per_warp = (per_warp + 7) / 8 * 8;
+    int wpc = (int)((220 * 1024) / per_warp);
+    if (wpc > 8) wpc = 8;
+    MWD_REQUIRE(wpc >= 1, "caption of %d tokens does not fit in shared memory", a.Tmax);
+    a.warps_per_cta = wpc;
+    const size_t smem = per_warp * wpc;
+    const int64_t grid = (npairs + wpc - 1) / wpc;
+    MWD_REQUIRE(grid <= 0x7fffffff, "too many pairs for one launch");
+    if (p->log_domain) {
+      MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hmm_align_kernel<true><<<(unsigned)grid, wpc * 32, smem, st>>>(a);
+    } else {
+      MWD_CHECK_CUDA(cudaFuncSetAttribute(hmm_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hmm_align_kernel<false><<<(unsigned)grid, wpc * 32, smem, st>>>(a);
+    }
+    MWD_CHECK_LAUNCH();
   }
-  MWD_CHECK_LAUNCH();
   return 0;
 }
 
