@@ -572,14 +572,22 @@ __global__ void __launch_bounds__(128) hmm_estep_packed_kernel(const HmmArgs a, 
 
 // ---------------------------------------------------------------- reductions
 // one warp per (concept, phone) table entry, over its postings
+// Entries with more than `big` postings (a frequent concept x a frequent phone on Zipf-distributed
+// corpora) would serialise on one warp: they are only listed here (big_list / big_count) and reduced
+// by the whole grid in hmm_postings_big_kernel.
 template <bool LOG>
 __global__ void hmm_postings_kernel(const double* __restrict__ post, const int64_t* __restrict__ idx,
                                     const int64_t* __restrict__ off, int64_t entries,
-                                    double* __restrict__ out) {
+                                    double* __restrict__ out, int64_t big, int64_t* __restrict__ big_list,
+                                    unsigned long long* __restrict__ big_count) {
   const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (e >= entries) return;
   const int64_t lo = off[e], hi = off[e + 1];
+  if (hi - lo > big) {
+    if (lane == 0) big_list[atomicAdd(big_count, 1ull)] = e;
+    return;
+  }
   if (LOG) {
     double m = -INFINITY;
     for (int64_t q = lo + lane; q < hi; q += 32) m = fmax(m, post[idx[q]]);
@@ -757,6 +765,82 @@ __global__ void hmm_mstep_obs_kernel(const double* __restrict__ obsC, double* __
     s = warp_sum(s);
     for (int fw = lane; fw < Vf; fw += 32)
       if (obs[base + fw] == obs[base + fw]) obs[base + fw] = obsC[base + fw] / s;    // :288-296
+  }
+}
+
+// ---------------------------------------------------------------- postings: large entries
+constexpr int kPostSplit = 128;     // slices (= CTAs) per large entry
+constexpr int kPostThreads = 256;
+
+// CTA s reduces slice s of every listed entry: slices are cut by position, threads stride the slice,
+// lanes / warps combine in fixed order -> the value does not depend on the order of the list.
+// part[b][s] = {max, sum exp(v - max)} (LOG) or {0, sum}.
+template <bool LOG>
+__global__ void __launch_bounds__(kPostThreads) hmm_postings_big_kernel(
+    const double* __restrict__ post, const int64_t* __restrict__ idx, const int64_t* __restrict__ off,
+    const int64_t* __restrict__ big_list, const unsigned long long* __restrict__ big_count,
+    double* __restrict__ part) {
+  __shared__ double s_w[kPostThreads / 32];
+  __shared__ double s_b;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nbig = (int64_t)*big_count;
+  auto cta_reduce = [&](double v, bool is_max) -> double {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_w[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = s_w[0];
+      for (int w = 1; w < kPostThreads / 32; ++w) t = is_max ? fmax(t, s_w[w]) : t + s_w[w];
+      s_b = t;
+    }
+    __syncthreads();
+    return s_b;
+  };
+  for (int64_t b = 0; b < nbig; ++b) {
+    const int64_t e = big_list[b];
+    const int64_t lo = off[e], len = off[e + 1] - lo;
+    const int64_t q0 = lo + len * blockIdx.x / kPostSplit, q1 = lo + len * (blockIdx.x + 1) / kPostSplit;
+    double m = 0.0;
+    if (LOG) {
+      double v = -INFINITY;
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += kPostThreads) v = fmax(v, post[idx[q]]);
+      m = cta_reduce(v, true);
+    }
+    double sacc = 0.0;
+    if (!(LOG && m == -INFINITY))
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += kPostThreads) {
+        const double v = post[idx[q]];
+        sacc += LOG ? exp(v - m) : v;
+      }
+    sacc = cta_reduce(sacc, false);
+    if (threadIdx.x == 0) {
+      part[(b * kPostSplit + blockIdx.x) * 2] = m;
+      part[(b * kPostSplit + blockIdx.x) * 2 + 1] = sacc;
+    }
+  }
+}
+
+// one thread per listed entry: slices combined in slice order
+template <bool LOG>
+__global__ void hmm_postings_big_combine_kernel(const int64_t* __restrict__ big_list,
+                                                const unsigned long long* __restrict__ big_count,
+                                                const double* __restrict__ part, double* __restrict__ out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= (int64_t)*big_count) return;
+  const double* pb = part + b * kPostSplit * 2;
+  if (LOG) {
+    double M = -INFINITY;
+    for (int s2 = 0; s2 < kPostSplit; ++s2) M = fmax(M, pb[2 * s2]);
+    if (M == -INFINITY) { out[big_list[b]] = -INFINITY; return; }
+    double S = 0.0;
+    for (int s2 = 0; s2 < kPostSplit; ++s2)
+      if (pb[2 * s2] != -INFINITY) S += pb[2 * s2 + 1] * exp(pb[2 * s2] - M);
+    out[big_list[b]] = log(S) + M;
+  } else {
+    double S = 0.0;
+    for (int s2 = 0; s2 < kPostSplit; ++s2) S += pb[2 * s2 + 1];
+    out[big_list[b]] = S;
   }
 }
 
@@ -1224,14 +1308,46 @@ extern "C" int mwd_hmm_reduce(const mwd_hmm_problem* p, const int64_t* post_idx,
     if (!seen) la.lens[la.n++] = m;
   }
   const unsigned fg = (unsigned)((ie + te + 255) / 256);
+  // observation counts over the postings index; entries past `big` postings go through the split path
+  const bool want_obs = !(p->log_domain && p->emis) && oe > 0;
+  ScratchGuard guard(st);
+  if (want_obs) {
+    int64_t big = p->n_slots / 1024;
+    if (big < 8192) big = 8192;
+    if (const char* be = getenv("MWD_HMM_POST_BIG")) big = atoll(be);
+    if (big < 1) big = 1;
+    while ((p->n_slots / big + 1) * kPostSplit * 16 > (int64_t(1) << 30)) big *= 2;   // bound the scratch
+    const int64_t cap = p->n_slots / big + 1;                 // most entries that can exceed `big`
+    const size_t list_bytes = ((size_t)cap * sizeof(int64_t) + 15) / 16 * 16;
+    cudaMemPool_t pool;
+    if (int rc = scratch_pool(&pool)) return rc;
+    MWD_CHECK_CUDA(cudaMallocFromPoolAsync(&guard.ptr, 16 + list_bytes + (size_t)cap * kPostSplit * 2 * sizeof(double),
+                                           pool, st));
+    auto* big_count = static_cast<unsigned long long*>(guard.ptr);
+    auto* big_list = reinterpret_cast<int64_t*>(static_cast<char*>(guard.ptr) + 16);
+    auto* part = reinterpret_cast<double*>(static_cast<char*>(guard.ptr) + 16 + list_bytes);
+    MWD_CHECK_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
+    if (p->log_domain) {
+      hmm_postings_kernel<true><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts, big, big_list, big_count);
+      hmm_postings_big_kernel<true><<<kPostSplit, kPostThreads, 0, st>>>(p->post, post_idx, post_off, big_list,
+                                                                        big_count, part);
+      hmm_postings_big_combine_kernel<true><<<(unsigned)((cap + 127) / 128), 128, 0, st>>>(big_list, big_count,
+                                                                                         part, counts);
+    } else {
+      hmm_postings_kernel<false><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts, big, big_list, big_count);
+      hmm_postings_big_kernel<false><<<kPostSplit, kPostThreads, 0, st>>>(p->post, post_idx, post_off, big_list,
+                                                                         big_count, part);
+      hmm_postings_big_combine_kernel<false><<<(unsigned)((cap + 127) / 128), 128, 0, st>>>(big_list, big_count,
+                                                                                          part, counts);
+    }
+    MWD_CHECK_LAUNCH();
+  }
   if (p->log_domain) {
-    if (!p->emis) hmm_postings_kernel<true><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
     hmm_fill_kernel<<<fg, 256, 0, st>>>(counts + oe, ie + te, -INFINITY);
     if (la.n)
       hmm_reduce_blocks_kernel<true><<<2 * la.n, kReduceThreads, 0, st>>>(la, p->part_init, p->part_trans, rows,
                                                                         counts + oe, counts + oe + ie);
   } else {
-    hmm_postings_kernel<false><<<og, 256, 0, st>>>(p->post, post_idx, post_off, oe, counts);
     hmm_fill_kernel<<<fg, 256, 0, st>>>(counts + oe, ie + te, 0.0);
     if (la.n)
       hmm_reduce_blocks_kernel<false><<<2 * la.n, kReduceThreads, 0, st>>>(la, p->part_init, p->part_trans, rows,

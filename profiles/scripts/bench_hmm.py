@@ -22,6 +22,8 @@ def main():
     ap.add_argument('--pairs', type=int, default=200000)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=2)
+    ap.add_argument('--zipf', type=float, default=0.0,
+                    help='>0: concept and phone ids drawn from Zipf(s) unigrams instead of uniformly')
     ap.add_argument('--domain', choices=('both', 'prob', 'log'), default='both')
     args = ap.parse_args()
     import torch
@@ -31,8 +33,16 @@ def main():
     pmf = np.array([0.12, 0.28, 0.27, 0.17, 0.09, 0.04, 0.02, 0.01])
     ns = rng.choice(8, size=args.pairs, p=pmf) + 1
     Ts = np.clip(np.round(rng.normal(49, 13, args.pairs)), 15, 125).astype(np.int64)
-    tgt = [rng.integers(0, Vt, n) for n in ns]
-    src = [rng.integers(0, Vf, T) for T in Ts]
+    if args.zipf > 0:
+        pt = 1.0 / np.arange(1, Vt + 1) ** args.zipf
+        pf = 1.0 / np.arange(1, Vf + 1) ** args.zipf
+        all_t = rng.choice(Vt, size=int(ns.sum()), p=pt / pt.sum())
+        all_f = rng.choice(Vf, size=int(Ts.sum()), p=pf / pf.sum())
+        tgt = np.split(all_t, np.cumsum(ns)[:-1])
+        src = np.split(all_f, np.cumsum(Ts)[:-1])
+    else:
+        tgt = [rng.integers(0, Vt, n) for n in ns]
+        src = [rng.integers(0, Vf, T) for T in Ts]
     pk = PackedSentences(tgt, src, Vf)
     for log_domain in {'both': (False, True), 'prob': (False,), 'log': (True,)}[args.domain]:
         eng = PlainHMMEngine(pk, Vt, Vf, log_domain)

@@ -17,9 +17,14 @@ def _unsort(pk, arr, off):
     return np.concatenate(out)
 
 
+@pytest.mark.parametrize('split_postings', [False, True])
 @pytest.mark.parametrize('case', HMM_CASES)
-def test_hmm_em_matches_reference_golden(case):
+def test_hmm_em_matches_reference_golden(case, split_postings, monkeypatch):
     from multimodalworddiscovery_b200.engine_hmm import PackedSentences, PlainHMMEngine
+    if split_postings:
+        # every (concept, phone) entry with more than 4 postings goes through the grid-wide split
+        # reduction that normally only serves the few huge entries of a Zipf-distributed corpus
+        monkeypatch.setenv('MWD_HMM_POST_BIG', '4')
     g = load_hmm(case)
     tgt, src, Vt, Vf = g['tgt_list'], g['src_list'], g['Vt'], g['Vf']
     lens = [int(m) for m in g['lens']]
