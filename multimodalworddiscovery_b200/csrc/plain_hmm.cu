@@ -1118,6 +1118,65 @@ __global__ void __launch_bounds__(128) gauss_stats_kernel(
   }
 }
 
+// Sliced form (the default): CTA (w, s) accumulates slice s of word w's postings -- slices are cut by
+// position, so the hot words of a corpus (NULL is a state of EVERY utterance) spread over the grid
+// instead of serialising one CTA.  Per 128-posting tile the weights exp(post + resp) are computed once,
+// one per thread, and shared; thread d then walks the tile for its dimension (coalesced embedding rows).
+// part[w][s][m] = {sum wgt, sum wgt*x (D), sum wgt*x^2 (D)}; gauss_stats_combine_kernel adds the slices
+// in slice order.
+template <typename FT>
+__global__ void __launch_bounds__(128) gauss_stats_slice_kernel(
+    const int64_t* __restrict__ word_idx, const int64_t* __restrict__ word_off,
+    const int32_t* __restrict__ slot_row, const FT* __restrict__ emb, int D, int M,
+    const double* __restrict__ post, const double* __restrict__ resp, double* __restrict__ part) {
+  const int w = blockIdx.x, sl = blockIdx.y, S = gridDim.y;
+  const int64_t lo0 = word_off[w], len = word_off[w + 1] - lo0;
+  const int64_t lo = lo0 + len * sl / S, hi = lo0 + len * (sl + 1) / S;
+  const int SW = 1 + 2 * D;
+  __shared__ double s_wg[128];
+  __shared__ int32_t s_row[128];
+  for (int m = 0; m < M; ++m) {
+    double* out = part + (((size_t)w * S + sl) * M + m) * SW;
+    for (int d0 = 0; d0 < D; d0 += 128) {
+      const int d = d0 + threadIdx.x;
+      double sx = 0.0, sxx = 0.0, sw = 0.0;
+      for (int64_t q0 = lo; q0 < hi; q0 += 128) {
+        const int cnt = (int)((hi - q0 < 128) ? hi - q0 : 128);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+          const int64_t slot = word_idx[q0 + threadIdx.x];
+          s_wg[threadIdx.x] = exp(post[slot] + resp[slot * M + m]);
+          s_row[threadIdx.x] = slot_row[slot];
+        }
+        __syncthreads();
+        if (d < D)
+          for (int i = 0; i < cnt; ++i) {
+            const double wg = s_wg[i];
+            const double xv = (double)emb[(size_t)s_row[i] * D + d];
+            sw += wg;
+            sx = fma(wg, xv, sx);
+            sxx = fma(wg, xv * xv, sxx);
+          }
+      }
+      if (d < D) {
+        out[1 + d] = sx;
+        out[1 + D + d] = sxx;
+        if (d == 0) out[0] = sw;
+      }
+    }
+  }
+}
+
+__global__ void gauss_stats_combine_kernel(const double* __restrict__ part, int S, int row_len,
+                                           double* __restrict__ stats) {
+  // blockIdx.x = w; row_len = M * (1 + 2D)
+  for (int e = threadIdx.x; e < row_len; e += blockDim.x) {
+    double t = 0.0;
+    for (int sl = 0; sl < S; ++sl) t += part[((size_t)blockIdx.x * S + sl) * row_len + e];
+    stats[(size_t)blockIdx.x * row_len + e] = t;
+  }
+}
+
 __global__ void gauss_update_kernel(int M, int D, const double* __restrict__ stats, int update_var,
                                     double* __restrict__ lprior, double* __restrict__ means,
                                     double* __restrict__ var) {
@@ -1487,6 +1546,27 @@ extern "C" int mwd_hmm_gauss_stats(const mwd_hmm_problem* p, const void* emb, in
                                    double* stats, void* stream) {
   cudaStream_t st = as_stream(stream);
   MWD_REQUIRE(p->slot_row != nullptr, "segment model needs slot_row");
+  const char* sp_env = getenv("MWD_GAUSS_STATS_SPLIT");
+  if (!(sp_env && atoi(sp_env) == 0) && p->n_tgt_types > 0) {
+    const int row_len = M * (1 + 2 * D);
+    int S = 32;
+    while (S > 1 && (size_t)p->n_tgt_types * S * row_len * sizeof(double) > (size_t(1) << 30)) S /= 2;
+    ScratchGuard guard(st);
+    cudaMemPool_t pool;
+    if (int rc = scratch_pool(&pool)) return rc;
+    MWD_CHECK_CUDA(cudaMallocFromPoolAsync(&guard.ptr, (size_t)p->n_tgt_types * S * row_len * sizeof(double), pool, st));
+    double* part = static_cast<double*>(guard.ptr);
+    const dim3 grid((unsigned)p->n_tgt_types, (unsigned)S);
+    if (emb_is_f64)
+      gauss_stats_slice_kernel<double><<<grid, 128, 0, st>>>(word_idx, word_off, p->slot_row, (const double*)emb, D, M,
+                                                            p->post, resp, part);
+    else
+      gauss_stats_slice_kernel<float><<<grid, 128, 0, st>>>(word_idx, word_off, p->slot_row, (const float*)emb, D, M,
+                                                           p->post, resp, part);
+    gauss_stats_combine_kernel<<<p->n_tgt_types, 128, 0, st>>>(part, S, row_len, stats);
+    MWD_CHECK_LAUNCH();
+    return 0;
+  }
   if (emb_is_f64)
     gauss_stats_kernel<double><<<p->n_tgt_types, 128, 0, st>>>(word_idx, word_off, p->slot_row, (const double*)emb,
                                                               D, M, p->post, resp, stats);
