@@ -330,7 +330,10 @@ int mwd_hmm_warps(void);
 /* forward + backward + updateInitialCounts + updateTransitionCounts + state posteriors:
  * hmm_word_discoverer.py:110-203 / audio_hmm_word_discoverer.py:148-254 (incl. its quirks:
  * un-normalised init counts, transition counts from the last t only).  Accumulates into
- * part_init / part_trans (zero / -inf them first), writes pair_ll and post.                  */
+ * part_init / part_trans (zero / -inf them first), writes pair_ll and post.
+ * Transient device scratch (the alpha lattices of the resident warps; in mwd_hmm_reduce and
+ * mwd_hmm_gauss_stats the split-reduction partials) comes from a stream-ordered memory pool the
+ * library owns per device and is returned to it, in stream order, before the call returns.   */
 int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream);
 
 /* Deterministic reduction of the partials and of the posteriors through a static postings
