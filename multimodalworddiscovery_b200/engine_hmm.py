@@ -22,6 +22,22 @@ def _np_ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
+def _stable_argsort_u16_digits(keys, bound):
+    """Stable argsort of non-negative integer keys < bound, as LSD passes over 16-bit digits: numpy's
+    stable sort is a radix sort only for 16-bit types, and the postings index of a 1 M-pair corpus has
+    1.5e8 keys (2.8x faster than a merge sort of the int64 keys)."""
+    idx = None
+    shift = 0
+    while shift == 0 or (bound - 1) >> shift:
+        digit = ((keys >> shift) & 0xffff).astype(np.uint16)
+        if idx is None:
+            idx = np.argsort(digit, kind='stable')
+        else:
+            idx = idx[np.argsort(digit[idx], kind='stable')]
+        shift += 16
+    return idx.astype(np.int64)
+
+
 class PackedSentences(object):
     """(concept states, phone tokens) pairs sorted by (n, T), CSR-packed, with postings."""
 
@@ -87,7 +103,7 @@ class PackedSentences(object):
         keys = self.tgt[tgt_idx].astype(np.int64) * self.Vf + self.src[pos_of_slot].astype(np.int64)
         self.slot_row = pos_of_slot.astype(np.int32)      # source row (phone position / segment) of each slot
         self.row_pair = pair_of_pos.astype(np.int32)      # pair of each source row
-        idx = np.argsort(keys, kind='stable').astype(np.int64)
+        idx = _stable_argsort_u16_digits(keys, n_tgt_types * self.Vf)
         off = np.searchsorted(keys[idx], np.arange(n_tgt_types * self.Vf + 1)).astype(np.int64)
         return idx, off
 

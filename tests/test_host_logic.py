@@ -163,3 +163,13 @@ def test_segembed_batched_embedding_equals_per_segment_oracle():
     # landmarks past maxLen collapse into one closing boundary (reference :68-76)
     assert _clip_landmarks(np.array([0, 5, 9, 14, 30]), 10) == [0, 5, 9, 10]
     assert _clip_landmarks(np.array([0, 5, 9]), 10) == [0, 5, 9]
+
+
+def test_radix_digit_argsort_matches_numpy_stable():
+    """The postings index is built with LSD passes over 16-bit digits; it must be THE stable order."""
+    from multimodalworddiscovery_b200.engine_hmm import _stable_argsort_u16_digits
+    rng = np.random.default_rng(3)
+    for bound in (1, 7, 65536, 65537, 1546 * 69, (1 << 33) + 11):
+        keys = rng.integers(0, bound, 50000).astype(np.int64)
+        assert np.array_equal(_stable_argsort_u16_digits(keys, bound), np.argsort(keys, kind='stable'))
+    assert _stable_argsort_u16_digits(np.zeros(0, np.int64), 5).shape == (0,)
