@@ -339,7 +339,8 @@ int mwd_hmm_estep(const mwd_hmm_problem* p, void* stream);
 /* Deterministic reduction of the partials and of the posteriors through a static postings
  * index (post_idx sorted by table entry, post_off[Vt*Vf+1]):
  *   counts = [ obsC (Vt x Vf) | initC ((NMAX+1) x NMAX) | transC ((NMAX+1) x NMAX^2) | sum LL ]
- * sums in the prob domain, log-sum-exp in the log domain.                                    */
+ * sums in the prob domain, log-sum-exp in the log domain.  p->n_slots must equal
+ * post_off[Vt*Vf] (it bounds the list of entries that take the split reduction).             */
 int64_t mwd_hmm_counts_len(int n_tgt_types, int n_src_types);
 int mwd_hmm_reduce(const mwd_hmm_problem* p, const int64_t* post_idx, const int64_t* post_off,
                    double* counts, void* stream);
