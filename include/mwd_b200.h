@@ -105,6 +105,10 @@ typedef struct {
                                 (image_audio_gaussian_hmm_word_discoverer.py:369-371,414-415,449-451,
                                 :629-631): likelihood, gamma and xi are divided by their raw sums   */
   int32_t reserved0;
+  int32_t* concept_alignment;/* [dev] Ttot or NULL: argmax_k conceptCountsA[t][k] (first index on ties, the
+                                `concept_alignment` of printAlignment :628) written by mwd_ik_estep from
+                                the column sums it forms anyway -- 4 bytes per phone instead of the
+                                8K-byte conceptCountsA row                                          */
 } mwd_ik_problem;
 
 /* bytes of `scratch` mwd_ik_estep needs for this problem (depends on t_max, bucket_n, K) */
@@ -268,6 +272,18 @@ int mwd_write_alignment_files(const char* txt_path, const char* json_path, int64
                               const double* cluster_probs, int n_concepts, int is_phoneme);
 /* float.__repr__(v) into buf (NUL-terminated); returns the length or -1 (test hook of the writer) */
 int mwd_format_float_repr(double v, char* buf, int buf_len);
+
+/* Stream-ordered utilities of the host mirror (no reference counterpart: the reference zeroes its
+ * count dicts in Python, trainUsingEM :209-213, and sums the log-likelihood in
+ * computeAvgLogLikelihood :523-531; the rank combination belongs to the multi-GPU sharding).
+ *   mwd_fill_f64    p[0:n] = value (cudaMemsetAsync when value == 0)
+ *   mwd_sum_f64     out[0] = fixed-shape deterministic sum of x[0:n]; scratch256: >= 256 doubles
+ *   mwd_rank_reduce out[e] = sum_r gathered[r][e] in rank order (log_domain != 0: logsumexp over r,
+ *                   except entry ll_index, which stays a plain sum; pass -1 for none)             */
+int mwd_fill_f64(double* p, int64_t n, double value, void* stream);
+int mwd_sum_f64(const double* x, int64_t n, double* scratch256, double* out, void* stream);
+int mwd_rank_reduce(const double* gathered, int world, int64_t n, int log_domain, int64_t ll_index,
+                    double* out, void* stream);
 
 /* argmax_k rows[t][k] (first index on ties, NaN-aware like np.argmax) -- printAlignment :628 */
 int mwd_argmax_rows(const double* rows, int64_t n_rows, int n_cols, int32_t* out, void* stream);

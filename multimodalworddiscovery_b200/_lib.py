@@ -38,6 +38,7 @@ class IkProblem(C.Structure):
         ('part_phone', C.c_void_p), ('part_init', C.c_void_p), ('part_trans', C.c_void_p),
         ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64),
         ('stats', C.c_void_p), ('slot_off', C.c_void_p), ('no_floor', C.c_int32), ('reserved0', C.c_int32),
+        ('concept_alignment', C.c_void_p),
     ]
 
 
@@ -111,6 +112,9 @@ SYMBOLS = {
     'mwd_ik_decode': (_i, [C.POINTER(IkProblem), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'mwd_write_alignment_files': (_i, [C.c_char_p, C.c_char_p, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     'mwd_format_float_repr': (_i, [_d, C.c_char_p, _i]),
+    'mwd_fill_f64': (_i, [_vp, _i64, _d, _vp]),
+    'mwd_sum_f64': (_i, [_vp, _i64, _vp, _vp, _vp]),
+    'mwd_rank_reduce': (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp]),
     'mwd_argmax_rows': (_i, [_vp, _i64, _i, _vp, _vp]),
     'mwd_ik_forward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'mwd_ik_backward_dense': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -156,3 +156,29 @@ def dense_to_tables(it, tt, lens):
     trans = {int(m): np.array(tt[int(m), :int(m) * int(m)], dtype=np.float64).reshape(int(m), int(m))
              for m in lens}
     return init, trans
+
+
+def resolve_feature_dtype(spec, *array_lists):
+    """Device storage type of the feature matrices.  ``spec``: 'float64' | 'float32' | 'auto'.
+    'auto' (the class default) keeps the reference's float64 arithmetic exact: float32 storage is chosen
+    only when EVERY value survives the round trip through float32 unchanged (float32 .npz inputs, or
+    float64 arrays holding float32-representable values); anything else -- float64 .npz files, the
+    output of ``normalize_vfeat`` -- stays float64, so the tables and the bit-exact Viterbi paths are
+    those of the reference's inputs, not of rounded ones.  'float32' is an explicit opt-in to rounding."""
+    if spec == 'float64':
+        return np.float64
+    if spec == 'float32':
+        return np.float32
+    if spec != 'auto':
+        raise ValueError("feature_dtype must be 'auto', 'float32' or 'float64', not %r" % (spec,))
+    for arrays in array_lists:
+        for a in arrays:
+            a = np.asarray(a)
+            if a.dtype == np.float32 or a.size == 0:
+                continue
+            if a.dtype.kind != 'f' and a.dtype.kind not in 'iub':
+                return np.float64
+            with np.errstate(over='ignore', invalid='ignore'):
+                if not np.array_equal(a, a.astype(np.float32)):
+                    return np.float64
+    return np.float32

@@ -52,6 +52,25 @@ __device__ __forceinline__ void drain_column(double* tab, int K, int k, const in
     if (xs[s] >= 0) tab[xs[s] * K + k] = v[s];
 }
 
+// concept_alignment of the PP rows deferred by the previous step: warp w takes rows w, w + nwarps, ...
+// (argmax_k conceptCountsA[t][k], first index on ties, printAlignment :628)
+template <int PP>
+__device__ __forceinline__ void argmax_rows_deferred(int32_t* ca_out, int K, const long long* pos, const double* cA) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int s = warp; s < PP; s += nwarps) {
+    const long long at = pos[s];
+    if (at < 0) continue;
+    double bv = 0.0;
+    int bk = 0x7fffffff;
+    for (int k = lane; k < K; k += 32) {
+      const double v = cA[s * K + k];
+      if (bk == 0x7fffffff || argmax_better(v, bv)) { bv = v; bk = k; }
+    }
+    const int kbest = warp_argmax_nonneg(bv, bk);
+    if (lane == 0) ca_out[at] = kbest;
+  }
+}
+
 constexpr int kEstepThreadsPerSm = 480;   // register budget: 65536 / 480 = 136 per thread (3 x 160-thread CTAs)
 constexpr int estep_min_blocks(int nn) { return nn <= 0 ? 1 : (kEstepThreadsPerSm / (32 * nn) < 1 ? 1 : kEstepThreadsPerSm / (32 * nn)); }
 
@@ -91,6 +110,7 @@ ik_estep_kernel(const EstepArgs a) {
   int* s_x = reinterpret_cast<int*>(smem + o_x);
   __shared__ int s_T[PP];
   __shared__ int s_xs[2][PP];                             // phone id of the deferred row, -1 = none
+  __shared__ long long s_pos[2][PP];                      // its position p0 + t in the packed phone array, -1 = none
 
   // transition / initial tables of this n
   for (int e = tid; e < n * n; e += blockDim.x) {
@@ -146,6 +166,8 @@ ik_estep_kernel(const EstepArgs a) {
       s_T[slot] = T;
       s_xs[0][slot] = -1;
       s_xs[1][slot] = -1;
+      s_pos[0][slot] = -1;
+      s_pos[1][slot] = -1;
     }
     for (int t = i * kLanesPerRow + l8; t < T; t += n * kLanesPerRow)
       s_x[slot * TX + t] = a.phones[p0 + t];
@@ -319,7 +341,11 @@ ik_estep_kernel(const EstepArgs a) {
         if (tab_on)
           for (int k = tid; k < K; k += blockDim.x)
             drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
-        if (i == 0 && l8 == 0) s_xs[par][slot] = act ? x : -1;
+        if (a.ca_out) argmax_rows_deferred<PP>(a.ca_out, K, s_pos[par ^ 1], s_cA + (par ^ 1) * PP * K);
+        if (i == 0 && l8 == 0) {
+          s_xs[par][slot] = act ? x : -1;
+          s_pos[par][slot] = act ? (long long)(p0 + t) : -1;
+        }
         if (act) {
           const double* ex = s_exch + exo;
           double wn = 0.0;
@@ -353,6 +379,7 @@ ik_estep_kernel(const EstepArgs a) {
       if (tab_on)
         for (int k = tid; k < K; k += blockDim.x)
           drain_column<PP>(tab, K, k, s_xs[par ^ 1], s_cA + (par ^ 1) * PP * K);
+      if (a.ca_out) argmax_rows_deferred<PP>(a.ca_out, K, s_pos[par ^ 1], s_cA + (par ^ 1) * PP * K);
     }
   }
 
@@ -710,6 +737,7 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     a.obsT = p->obsT;
     a.pair_ll = p->pair_ll;
     a.cA_out = p->concept_counts_a;
+    a.ca_out = p->concept_alignment;
     a.part_phone = p->part_phone;
     a.part_init = p->part_init;
     a.part_trans = p->part_trans;

@@ -285,6 +285,15 @@ __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp
         for (int m = 0; m < KC; ++m)
           if (lane + 32 * m < K) crow[32 * m] = cs[m];
       }
+      if (a.ca_out) {     // concept_alignment[t] = argmax_k cA[t][k] (first index on ties, :628)
+        double bv = 0.0;
+        int bk = 0x7fffffff;
+#pragma unroll
+        for (int m = 0; m < KC; ++m)
+          if (lane + 32 * m < K && (bk == 0x7fffffff || argmax_better(cs[m], bv))) { bv = cs[m]; bk = lane + 32 * m; }
+        const int kbest = warp_argmax_nonneg(bv, bk);
+        if (lane == 0) a.ca_out[p0 + t] = kbest;
+      }
     };
     auto drop_slice = [&](int c) {
       // checkpoint slice c is dead: drop it from L2 instead of letting it be written back

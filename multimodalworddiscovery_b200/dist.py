@@ -27,6 +27,16 @@ def fixed_order_allreduce(buf, group=None, log_domain=False, ll_index=None):
     world = dist.get_world_size(group)
     flat = torch.empty((world * buf.numel(),), dtype=buf.dtype, device=buf.device)
     dist.all_gather_into_tensor(flat, buf.reshape(-1), group=group)
+    if buf.is_cuda:
+        # product path: one kernel of libmwd_b200.so, rank order fixed
+        import ctypes as C
+        from . import _lib
+        st = C.c_void_p(torch.cuda.current_stream(buf.device).cuda_stream)
+        _lib.check(_lib.load().mwd_rank_reduce(C.c_void_p(flat.data_ptr()), world, buf.numel(), 1 if log_domain else 0,
+                                               -1 if ll_index is None else int(ll_index),
+                                               C.c_void_p(buf.data_ptr()), st))
+        return buf
+    # CPU tensors: only the gloo host-logic tests (tests/test_dist_gloo.py) come through here
     g = flat.view(world, buf.numel())
     if log_domain:
         ll = g[:, ll_index].sum() if ll_index is not None else None

@@ -26,7 +26,7 @@ class IKEngine(object):
     """Holds one rank's packed shard, the model parameters and all workspaces in HBM."""
 
     def __init__(self, packed, n_concepts, n_phone_types, gaussian=False, device=None,
-                 keep_concept_counts_a=True, process_group=None, hidden_dim=0):
+                 keep_concept_counts_a=False, process_group=None, hidden_dim=0):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -78,7 +78,13 @@ class IKEngine(object):
         self.pz = torch.empty((max(R, 1), self.K), dtype=f64, device=dev)
         self.cC = torch.empty((max(R, 1), self.K), dtype=f64, device=dev)
         self.pair_ll = torch.zeros((max(N, 1),), dtype=f64, device=dev)
+        # conceptCountsA (Ttot x K float64, 26 KB per MSCOCO pair) is only materialised on request
+        # (materialize_cA); what printAlignment needs of it -- its row argmax -- is written by the
+        # E-step kernel itself into `ca` (4 bytes per phone)
         self.cA = torch.empty((max(Tt, 1), self.K), dtype=f64, device=dev) if keep_concept_counts_a else None
+        self.ca = torch.empty((max(Tt, 1),), dtype=torch.int32, device=dev)
+        self._ca_valid = False
+        self._prev = None      # parameters that ENTERED the last EM iteration (device snapshot)
         # partial tables + reduced buffer [counts | grad] (the all-reduce unit)
         ps = PartialSizes()
         _lib.check(self.lib.mwd_ik_partial_sizes(self.K, self.P, C.byref(ps)))
@@ -115,6 +121,8 @@ class IKEngine(object):
         need = int(self.lib.mwd_ik_scratch_bytes(C.byref(prob)))
         self.scratch = torch.empty((max(need, 8) // 8 + 1,), dtype=f64, device=dev)
         self.last_counts = None
+        self._sum_scratch = torch.empty((256,), dtype=f64, device=dev)
+        self._ll_out = torch.zeros((2,), dtype=f64, device=dev)   # [0]: loglik_sum, [1]: LL of the last EM iteration
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -135,7 +143,8 @@ class IKEngine(object):
         p.init, p.trans, p.obsT = _ptr(self.init_t), _ptr(self.trans_t), _ptr(self.obsT)
         p.pz, p.concept_counts = _ptr(self.pz), _ptr(self.cC)
         p.pair_ll = _ptr(self.pair_ll)
-        p.concept_counts_a = _ptr(self.cA) if with_cA else C.c_void_p(0)
+        p.concept_counts_a = _ptr(self.cA) if (with_cA and self.cA is not None) else C.c_void_p(0)
+        p.concept_alignment = _ptr(self.ca)
         p.part_phone, p.part_init = _ptr(self._part_phone), _ptr(self._part_init)
         p.part_trans = _ptr(self._part_trans)
         p.scratch = _ptr(self.scratch)
@@ -197,8 +206,18 @@ class IKEngine(object):
         """Sum over this shard of log(max(p(x|y), EPS)) under the current parameters (device scalar)."""
         self.posterior(width)
         prob = self._problem()
-        _lib.check(self.lib.mwd_ik_loglik(C.byref(prob), self._stream()))
-        return self.pair_ll[:self.pk.n_pairs].sum()
+        st = self._stream()
+        _lib.check(self.lib.mwd_ik_loglik(C.byref(prob), st))
+        _lib.check(self.lib.mwd_sum_f64(_ptr(self.pair_ll), self.pk.n_pairs, _ptr(self._sum_scratch),
+                                        _ptr(self._ll_out), st))
+        return self._ll_out[0]
+
+    def _zero_partials(self):
+        _lib.check(self.lib.mwd_fill_f64(_ptr(self.part), self.part.numel(), 0.0, self._stream()))
+
+    def _ll_scalar(self):
+        """The reduced sum of log-likelihoods of the last E-step (a view: consume before the next one)."""
+        return self.counts[self.counts_len - 1]
 
     def estep(self, width=1.0, with_cA=True, timers=None):
         """E-step over the shard: fills pz, pair_ll, cC, (cA) and the reduced [counts | grad].
@@ -216,10 +235,12 @@ class IKEngine(object):
             e1.record()
             timers.append((name, e0, e1))
 
-        self.part.zero_()
+        self._zero_partials()
         timed('posterior', lambda: self.posterior(width))
         prob = self._problem(with_cA=with_cA and self.cA is not None)
         timed('ik_estep', lambda: _lib.check(lib.mwd_ik_estep(C.byref(prob), st)))
+        self._ca_valid = True
+        self._cA_fresh = bool(with_cA and self.cA is not None)
         timed('ik_concept', lambda: _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st)))
         timed('reduce_counts', lambda: _lib.check(lib.mwd_ik_reduce_counts(C.byref(prob), _ptr(self.counts), st)))
         if self.two_layer:
@@ -251,6 +272,68 @@ class IKEngine(object):
         per_chunk = sum(post + 3 * len(ch['bucket_n']) + 1 for ch in self.plan_chunks(n_chunks))
         return per_chunk + 8 + 1 + 3
 
+    # ------------------------------------------------------------------ parameter snapshots (device to device)
+    def _param_tensors(self):
+        ts = [self.init_t, self.trans_t, self.obsT, self.post]
+        if self.two_layer:
+            ts.append(self.V_t)
+        return ts
+
+    def _copy_params(self, dst, src):
+        for d, s_ in zip(dst, src):
+            d.copy_(s_)
+
+    def _snapshot_entering(self, width):
+        """Keep the parameters an EM iteration starts from: conceptCountsA of that iteration can then be
+        materialised later without having been stored (materialize_cA)."""
+        if self._prev is None:
+            self._prev = [self.torch.empty_like(t) for t in self._param_tensors()]
+        self._copy_params(self._prev, self._param_tensors())
+        self._prev_width = width
+
+    def snapshot(self):
+        """simulatedAnnealing's init_prev / trans_prev / obs_prev / W_prev (:169-172) as device copies."""
+        if getattr(self, '_sa_snap', None) is None:
+            self._sa_snap = [self.torch.empty_like(t) for t in self._param_tensors()]
+        self._copy_params(self._sa_snap, self._param_tensors())
+
+    def restore_snapshot(self):
+        self._copy_params(self._param_tensors(), self._sa_snap)
+
+    def perturb_posterior(self, noise, scale):
+        """W (or mus) += scale * noise  (:173); ``noise``: host array drawn by the caller's RNG."""
+        nz = self.torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(self.device)
+        if tuple(nz.shape) != tuple(self.post.shape):
+            raise ValueError('noise shape %s != %s' % (tuple(nz.shape), tuple(self.post.shape)))
+        _lib.check(self.lib.mwd_sgd_update(_ptr(self.post), _ptr(nz), self.post.numel(), 1.0, float(scale), 0.0,
+                                           self._stream()))
+
+    def materialize_cA(self):
+        """conceptCountsA (Ttot x K) of the LAST E-step, recomputed on demand from the parameters that
+        entered it (same kernels, same launch shapes -> the values the E-step would have stored)."""
+        if self.cA is not None and self._ca_valid and getattr(self, '_cA_fresh', False):
+            return self.cA
+        if self._prev is None:
+            raise MwdError('no E-step has run yet')
+        torch = self.torch
+        if self.cA is None:
+            self.cA = torch.empty((max(self.pk.n_phones_total, 1), self.K), dtype=torch.float64, device=self.device)
+        cur = [t.clone() for t in self._param_tensors()]
+        self._copy_params(self._param_tensors(), self._prev)
+        self.posterior(self._prev_width)
+        prob = self._problem(with_cA=True)
+        prob.part_phone = C.c_void_p(0)          # counts of this pass are not wanted ...
+        self._zero_partials()                    # ... and init / trans partials are scratch by now
+        _lib.check(self.lib.mwd_ik_estep(C.byref(prob), self._stream()))
+        self._copy_params(self._param_tensors(), cur)
+        self._cA_fresh = True
+        return self.cA
+
+    def _keep_ll(self):
+        """Park the iteration's summed log-likelihood (device-to-device copy, no kernel)."""
+        self._ll_out[1:2].copy_(self.counts[self.counts_len - 1:self.counts_len])
+        return self._ll_out[1]
+
     def allreduce(self):
         """Sum [counts | grad] over ranks: all_gather + fixed-rank-order sum (bitwise reproducible)."""
         fixed_order_allreduce(self.reduced, self.pg)
@@ -279,9 +362,10 @@ class IKEngine(object):
     def em_iteration(self, lr, momentum, width=1.0, with_cA=True, timers=None, freeze_trans=False):
         """One epoch body of trainUsingEM.  Returns the device scalar sum of log-likelihoods
         (over ALL ranks) of the parameters that entered the iteration."""
+        self._snapshot_entering(width)
         self.estep(width, with_cA, timers)
         self.allreduce()
-        ll = self.counts[self.counts_len - 1].clone()
+        ll = self._keep_ll()
         self.mstep(lr, momentum, width, freeze_trans)
         return ll
 
@@ -358,7 +442,7 @@ class IKEngine(object):
                 ev.record(cs)
                 events.append(ev)
         st = self._stream()
-        self.part.zero_()
+        self._zero_partials()
         for c, (ch, ev) in enumerate(zip(chunks, events)):
             main.wait_event(ev)
             R = ch['r_hi'] - ch['r_lo']
@@ -379,7 +463,7 @@ class IKEngine(object):
         _lib.check(lib.mwd_ik_reduce_counts(C.byref(full), _ptr(self.counts), st))
         _lib.check(lib.mwd_ik_posterior_grad_finish(self.K, self.D, _ptr(self.grad_partials), _ptr(self.grad), st))
         self.allreduce()
-        ll = self.counts[self.counts_len - 1].clone()
+        ll = self._keep_ll()
         self.mstep(lr, momentum, width)
         return ll
 
@@ -420,17 +504,17 @@ class IKEngine(object):
         n, T = int(v.shape[0]), int(len(x))
         if not (1 <= n <= NMAX):
             raise ValueError('n=%d outside [1,%d]' % (n, NMAX))
-        dt = np.float64 if self.feat_is_f64 else np.float32
-        v_d = torch.from_numpy(np.ascontiguousarray(v, dtype=dt)).to(dev)
+        # single-pair API: features go up as float64 whatever the corpus storage type is (no rounding)
+        v_d = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
         x_d = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
         roff = torch.tensor([0, n], dtype=torch.int32, device=dev)
         poff = torch.tensor([0, T], dtype=torch.int32, device=dev)
         pz = torch.empty((n, self.K), dtype=torch.float64, device=dev)
         st = self._stream()
-        self._posterior_of(v_d, n, pz, width)
+        self._posterior_of(v_d, n, pz, width, is64=1)
         p = IkProblem()
         p.n_pairs, p.n_regions, p.n_phones_total = 1, n, T
-        p.feat_dim, p.feat_is_f64, p.n_concepts, p.n_phone_types = self.D, self.feat_is_f64, self.K, self.P
+        p.feat_dim, p.feat_is_f64, p.n_concepts, p.n_phone_types = self.D, 1, self.K, self.P
         p.t_max, p.n_buckets = T, 0
         p.region_off, p.phone_off, p.feats, p.phones = _ptr(roff), _ptr(poff), _ptr(v_d), _ptr(x_d)
         p.init, p.trans, p.obsT, p.pz = _ptr(self.init_t), _ptr(self.trans_t), _ptr(self.obsT), _ptr(pz)
@@ -450,13 +534,19 @@ class IKEngine(object):
         return (ali.cpu().numpy(), ap.cpu().numpy().reshape(T, n), ic.cpu().numpy(), cs.cpu().numpy())
 
     def concept_alignment(self):
-        """argmax_k conceptCountsA[t][k] for every phone of the shard (printAlignment :628)."""
-        if self.cA is None:
-            raise MwdError('conceptCountsA was not kept (keep_concept_counts_a=False)')
+        """argmax_k conceptCountsA[t][k] for every phone of the shard (printAlignment :628): written by
+        the last E-step itself, no conceptCountsA needed."""
+        if not self._ca_valid:
+            raise MwdError('no E-step has run yet')
+        return self.ca[:self.pk.n_phones_total]
+
+    def concept_alignment_from_cA(self):
+        """Same quantity from a materialised conceptCountsA (cross-check of the fused argmax)."""
+        cA = self.materialize_cA()
         torch = self.torch
         Tt = self.pk.n_phones_total
         out = torch.empty((max(Tt, 1),), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.mwd_argmax_rows(_ptr(self.cA), Tt, self.K, _ptr(out), self._stream()))
+        _lib.check(self.lib.mwd_argmax_rows(_ptr(cA), Tt, self.K, _ptr(out), self._stream()))
         return out[:Tt]
 
     def dense_sweep(self, pz_pair, phones_pair, backward=False, obsT=None):
@@ -480,22 +570,22 @@ class IKEngine(object):
     def posterior_rows(self, v, width=1.0):
         """softmaxLayer(vSen) for an arbitrary (n, D) feature block under the current parameters."""
         torch = self.torch
-        dt = np.float64 if self.feat_is_f64 else np.float32
-        v_d = torch.from_numpy(np.ascontiguousarray(v, dtype=dt)).to(self.device)
+        v_d = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(self.device)
         out = torch.empty((v.shape[0], self.K), dtype=torch.float64, device=self.device)
-        self._posterior_of(v_d, v.shape[0], out, width)
+        self._posterior_of(v_d, v.shape[0], out, width, is64=1)
         return out.cpu().numpy()
 
-    def _posterior_of(self, v_d, n, out, width=1.0):
+    def _posterior_of(self, v_d, n, out, width=1.0, is64=None):
         """softmaxLayer of an arbitrary device feature block under the current parameters."""
         lib, st = self.lib, self._stream()
+        is64 = self.feat_is_f64 if is64 is None else is64
         if self.two_layer:
             h = self.torch.empty((n, self.H), dtype=self.torch.float64, device=self.device)
-            _lib.check(lib.mwd_hidden_relu(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.V_t), self.H, _ptr(h), st))
+            _lib.check(lib.mwd_hidden_relu(_ptr(v_d), is64, n, self.D, _ptr(self.V_t), self.H, _ptr(h), st))
             _lib.check(lib.mwd_posterior_linear(_ptr(h), 1, n, self.H, _ptr(self.post), self.K, _ptr(out), st))
         elif self.gaussian:
-            _lib.check(lib.mwd_posterior_gaussian(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
+            _lib.check(lib.mwd_posterior_gaussian(_ptr(v_d), is64, n, self.D, _ptr(self.post),
                                                   float(width), self.K, _ptr(self.w_scratch), _ptr(out), st))
         else:
-            _lib.check(lib.mwd_posterior_linear(_ptr(v_d), self.feat_is_f64, n, self.D, _ptr(self.post),
+            _lib.check(lib.mwd_posterior_linear(_ptr(v_d), is64, n, self.D, _ptr(self.post),
                                                 self.K, _ptr(out), st))

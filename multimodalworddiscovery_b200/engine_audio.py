@@ -97,10 +97,12 @@ class IKAudioEngine(IKEngine):
 
     def estep(self, width=1.0, with_cA=True, timers=None):
         lib, st = self.lib, self._stream()
-        self.part.zero_()
+        self._zero_partials()
         self.posterior(width)
         prob = self._problem(with_cA=True)
         _lib.check(lib.mwd_ik_estep(C.byref(prob), st))
+        self._ca_valid = True
+        self._cA_fresh = True
         _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st))
         red = self._problem(with_cA=True)
         red.n_phone_types = self.nPh                  # layout of `counts`: phone block is nPhones x K

@@ -194,10 +194,10 @@ class PlainHMMEngine(object):
     # ------------------------------------------------------------------ kernels
     def estep(self, alpha=None, beta=None):
         fill = float('-inf') if self.log else 0.0
-        self.part_init.fill_(fill)
-        self.part_trans.fill_(fill)
-        prob = self._problem(alpha, beta)
         st = self._stream()
+        _lib.check(self.lib.mwd_fill_f64(_ptr(self.part_init), self.part_init.numel(), fill, st))
+        _lib.check(self.lib.mwd_fill_f64(_ptr(self.part_trans), self.part_trans.numel(), fill, st))
+        prob = self._problem(alpha, beta)
         _lib.check(self.lib.mwd_hmm_estep(C.byref(prob), st))
         _lib.check(self.lib.mwd_hmm_reduce(C.byref(prob), _ptr(self.post_idx), _ptr(self.post_off),
                                            _ptr(self.counts), st))

@@ -18,7 +18,7 @@ from copy import deepcopy
 import numpy as np
 
 from .. import _lib
-from ..corpus import pack_pairs
+from ..corpus import pack_pairs, resolve_feature_dtype
 
 EPS = 1e-50
 
@@ -192,7 +192,7 @@ class ImagePhoneHMMBase(object):
                  self.audioFeatDim)
         if getattr(self, '_eng', None) is None or self._eng_token != token:
             rank, world = self._dist()
-            dt = np.float64 if self._feature_dtype == 'float64' else np.float32
+            dt = resolve_feature_dtype(self._feature_dtype, self.vCorpus)
             pk = pack_pairs(self.vCorpus, self._phone_ids(), feat_dtype=dt, rank=rank, world=world)
             self._eng = IKEngine(pk, self.nWords, self.audioFeatDim, gaussian=self.GAUSSIAN,
                                  device=self._device, keep_concept_counts_a=self._keep_cA,
@@ -362,9 +362,9 @@ class ImagePhoneHMMBase(object):
         if getattr(self, '_conceptCountsA_cache', None) is None:
             if getattr(self, '_eng', None) is None or not getattr(self, '_cA_valid', False):
                 raise AttributeError("'%s' object has no attribute 'conceptCountsA'" % type(self).__name__)
-            if self._eng.cA is None:
-                raise _lib.MwdError('conceptCountsA was not kept: set modelConfigs["keep_concept_counts_a"]=True')
-            self._conceptCountsA_cache = self._gather_rows(self._eng.cA, self._eng.pk.phone_off)
+            # not stored by the E-step unless modelConfigs['keep_concept_counts_a']: recomputed here from the
+            # parameters that entered the last EM iteration (bit-identical, engine.materialize_cA)
+            self._conceptCountsA_cache = self._gather_rows(self._eng.materialize_cA(), self._eng.pk.phone_off)
         return self._conceptCountsA_cache
 
     @conceptCountsA.setter
@@ -448,11 +448,13 @@ class ImagePhoneHMMBase(object):
         if world == 1:
             return self._print_alignment_flat(filePrefix, isPhoneme, _zero_concept_alignment)
         alis, ics, aps, cas = self._decode_all(_zero_concept_alignment)
-        if rank != 0:
-            return
         concept_probs = None
         if self.GAUSSIAN:
+            # self.conceptCounts gathers over ranks (collective): every rank must take part BEFORE the
+            # non-zero ranks leave
             concept_probs = [np.asarray(c, dtype=np.float64) for c in self.conceptCounts]
+        if rank != 0:
+            return
         write_alignment_files(filePrefix, alis, ics, aps, concept_alignment=cas, concept_probs=concept_probs,
                               n_concepts=self.nWords, is_phoneme=isPhoneme)
 
@@ -486,31 +488,48 @@ class ImagePhoneHMMBase(object):
 
     # ------------------------------------------------------------------ simulated annealing
     def simulatedAnnealing(self, numIterations=100, T0=0.5, stepScale=5., debug=False):
-        """:159-196 (gaussian :156-193): same control flow, the EM inside runs on the GPU."""
-        inner = 5 if self.GAUSSIAN else 20
+        """:159-196 (gaussian :156-193).  Same accept / reject walk, same RNG draws (``np.random.normal`` for
+        the jump, ``random.random`` for the Boltzmann test) and the same prints and files as the reference,
+        but the model never leaves the GPU inside the loop: the reference's four ``deepcopy`` snapshots are
+        device-to-device copies (``engine.snapshot / restore_snapshot``), the jump is added by a kernel, the
+        inner EM iterations and the energy evaluation run on the resident tables, and the host attributes
+        (``init / trans / obs / W|mus``) are refreshed only where the reference lets a caller observe them
+        (``printModel`` / ``printAlignment`` on a new minimum, and on return)."""
+        inner = 5 if self.GAUSSIAN else 20                                   # :174 / gaussian :171
         self.trainUsingEM(numIterations=5, warmStart=False, printStatus=True)
-        E0 = -self.computeAvgLogLikelihood()
+        eng = self._push()
+        N = len(self.vCorpus)
+
+        def energy():                                                        # -computeAvgLogLikelihood()
+            return -float(self._allreduce_scalar(eng.loglik_sum(self._width()))) / N
+
+        E0 = energy()
         Emin = E0
         count = 0
+        self.sa_trace = []                                                   # (E1, E0 before the test, accepted)
+        shape = self._posterior_param().shape
         for epoch in range(numIterations):
             print('Simulated Annealing Iteration %d' % epoch)
             begin_time = time.time()
-            init_prev = deepcopy(self.init)
-            trans_prev = deepcopy(self.trans)
-            obs_prev = deepcopy(self.obs)
-            p_prev = deepcopy(self._posterior_param())
-            self._set_posterior_param(self._posterior_param()
-                                      + stepScale * np.random.normal(size=self._posterior_param().shape))
-            self.trainUsingEM(numIterations=inner, warmStart=True, printStatus=False)
-            E1 = -self.computeAvgLogLikelihood()
+            eng.snapshot()                                                   # init/trans/obs/W _prev (:169-172)
+            eng.perturb_posterior(np.random.normal(size=shape), stepScale)   # :173
+            # trainUsingEM(numIterations=inner, warmStart=True, printStatus=False) on the resident model (:174)
+            for it in range(inner):
+                eng.em_iteration(self.lr, self.momentum, self._width())
+                if (it + 1) % 10 == 0:
+                    self.lr /= 10
+            self._cA_valid = True
+            self._conceptCounts_cache = None
+            self._conceptCountsA_cache = None
+            np.save(self.modelName + '_likelihoods.npy', np.zeros((inner,)))
+            E1 = energy()
             print('Current and previous energy level: ', E1, E0)
             Tk = T0 / np.log(epoch + 2)
             if E1 > E0 and random.random() > np.exp(-(E1 - E0) / Tk):
-                self._set_posterior_param(p_prev)
-                self.init = init_prev
-                self.trans = trans_prev
-                self.obs = obs_prev
+                self.sa_trace.append((E1, E0, False))
+                eng.restore_snapshot()
             else:
+                self.sa_trace.append((E1, E0, True))
                 if debug:
                     print('Random jump at temperature %.5f' % Tk)
                 E0 = E1
@@ -519,6 +538,8 @@ class ImagePhoneHMMBase(object):
                     count += 1
                     print('Update %d after %.2f s: current lowest energy level is %.5f'
                           % (count, time.time() - begin_time, Emin))
+                    self._pull(eng)
                     self.printModel(self.modelName + '_%d' % count)
                     self.printAlignment(self.modelName + '_%d_alignment' % count, debug=False)
                     begin_time = time.time()
+        self._pull(eng)

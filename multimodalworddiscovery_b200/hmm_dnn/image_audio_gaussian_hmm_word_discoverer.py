@@ -44,7 +44,7 @@ class ImageAudioGaussianHMMWordDiscoverer(ImageAudioHMMWordDiscoverer):
     self.isExact = modelConfigs.get('is_exact', False)
     self.normalize_vfeat = modelConfigs.get('normalize_vfeat', False)
     self._device = modelConfigs.get('device', None)
-    self._feature_dtype = modelConfigs.get('feature_dtype', 'float32')
+    self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
     self._pair_limit = None                                   # this class reads the whole file (:66,:82)
     self.init = {}
     self.trans = {}
@@ -86,7 +86,8 @@ class ImageAudioGaussianHMMWordDiscoverer(ImageAudioHMMWordDiscoverer):
     token = (id(self.vCorpus), len(self.vCorpus), id(self.aCorpus), len(self.aCorpus), self.nWords, self.nPhones)
     if getattr(self, '_eng', None) is None or self._eng_token != token:
       rank, world = self._dist()
-      dt = np.float64 if self._feature_dtype == 'float64' else np.float32
+      from ..corpus import resolve_feature_dtype
+      dt = resolve_feature_dtype(self._feature_dtype, self.vCorpus, self.aCorpus)
       pk, audio = pack_audio_pairs(self.vCorpus, self.aCorpus, feat_dtype=dt, rank=rank, world=world)
       self._eng = IKAudioEngine(pk, audio, self.nWords, self.nPhones, device=self._device, gaussian=True)
       self._eng_token = token

@@ -50,7 +50,7 @@ class ImageAudioHMMWordDiscoverer(ImagePhoneHMMBase):
     self.imagePosteriorFile = modelConfigs.get('image_posterior_weights_file', None)
     # optional, B200-build-only keys
     self._device = modelConfigs.get('device', None)
-    self._feature_dtype = modelConfigs.get('feature_dtype', 'float32')
+    self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
     self._pair_limit = modelConfigs.get('pair_limit', 30)     # the reference's hard-wired [:30]
 
     self.init = {}
@@ -128,7 +128,8 @@ class ImageAudioHMMWordDiscoverer(ImagePhoneHMMBase):
     token = (id(self.vCorpus), len(self.vCorpus), id(self.aCorpus), len(self.aCorpus), self.nWords, self.nPhones)
     if getattr(self, '_eng', None) is None or self._eng_token != token:
       rank, world = self._dist()
-      dt = np.float64 if self._feature_dtype == 'float64' else np.float32
+      from ..corpus import resolve_feature_dtype
+      dt = resolve_feature_dtype(self._feature_dtype, self.vCorpus, self.aCorpus)
       pk, audio = pack_audio_pairs(self.vCorpus, self.aCorpus, feat_dtype=dt, rank=rank, world=world)
       self._eng = IKAudioEngine(pk, audio, self.nWords, self.nPhones, device=self._device)
       self._eng_token = token

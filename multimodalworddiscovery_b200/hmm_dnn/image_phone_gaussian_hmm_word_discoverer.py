@@ -34,8 +34,8 @@ class ImagePhoneGaussianHMMWordDiscoverer(ImagePhoneHMMBase):
     self.isExact = modelConfigs.get('is_exact', False)
     self.normalize_vfeat = modelConfigs.get('normalize_vfeat', False)   # read but ignored, as in the reference
     self._device = modelConfigs.get('device', None)
-    self._feature_dtype = modelConfigs.get('feature_dtype', 'float32')
-    self._keep_cA = modelConfigs.get('keep_concept_counts_a', True)
+    self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
+    self._keep_cA = modelConfigs.get('keep_concept_counts_a', False)   # conceptCountsA is materialised on access
     # The reference silently keeps only the first 30 pairs (debug leftover, :56,:87).  Default is
     # bug-compatible; set modelConfigs['max_pairs']=None to train on the whole corpus.
     self._max_pairs = modelConfigs.get('max_pairs', 30)
@@ -81,6 +81,15 @@ class ImagePhoneGaussianHMMWordDiscoverer(ImagePhoneHMMBase):
       self.mus = KMeans(n_clusters=self.nWords).fit(np.concatenate(self.vCorpus, axis=0)).cluster_centers_
     print("Finish initialization after %0.3f s" % (time.time() - begin_time))
     self.printUnimodalCluster(filePrefix=self.modelName)
+
+  def trainUsingEM(self, numIterations=20, writeModel=False, warmStart=False, convergenceEpsilon=0.01,
+                   printStatus=True, debug=False, **kw):
+    if self.isExact and numIterations > 0:
+      # reference :480-486: the closed-form anchor update reads conceptCount / zProb before assigning
+      # them, so the first M-step raises; there is no exact update to mirror
+      raise NameError("name 'conceptCount' is not defined")
+    ImagePhoneHMMBase.trainUsingEM(self, numIterations, writeModel, warmStart, convergenceEpsilon, printStatus,
+                                   debug, **kw)
 
   def printUnimodalCluster(self, filePrefix):
     """reference :663-678"""

@@ -35,7 +35,7 @@ class ImagePhoneHMMDNNWordDiscoverer(ImagePhoneHMMBase):
     self.imagePosteriorFile = modelConfigs.get('image_posterior_weights_file', None)
     self.normalize_vfeat = modelConfigs.get('normalize_vfeat', False)
     self._device = modelConfigs.get('device', None)
-    self._feature_dtype = modelConfigs.get('feature_dtype', 'float32')
+    self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
     self._keep_cA = False                      # the reference class keeps no conceptCountsA
 
     self.init = {}

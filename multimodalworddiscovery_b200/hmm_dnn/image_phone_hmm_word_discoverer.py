@@ -38,8 +38,8 @@ class ImagePhoneHMMWordDiscoverer(ImagePhoneHMMBase):
     self.imagePosteriorFile = modelConfigs.get('image_posterior_weights_file', None)
     # optional, B200-build-only keys (defaults keep unchanged drivers working)
     self._device = modelConfigs.get('device', None)
-    self._feature_dtype = modelConfigs.get('feature_dtype', 'float32')
-    self._keep_cA = modelConfigs.get('keep_concept_counts_a', True)
+    self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
+    self._keep_cA = modelConfigs.get('keep_concept_counts_a', False)   # conceptCountsA is materialised on access
 
     self.init = {}
     self.trans = {}

@@ -3,17 +3,25 @@
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
 
-PARITY UNPINNED for this file: hmm/audio_segembed_hmm_word_discoverer.py constructs its acoustic
-model as ``acousticModel(numMixtures, frameDim, fCorpus=..., tCorpus=..., ...)`` (:86-92) but the shipped
-``AudioHMMWordDiscoverer`` only accepts a corpus FILE (its matching constructor is the commented line
-audio_hmm_word_discoverer.py:15) -> TypeError, so the reference cannot run this path and ships no
-vectors for it.  What is restated here, piece by piece, from code that does exist:
+PINNED PIECE BY PIECE.  hmm/audio_segembed_hmm_word_discoverer.py cannot run end to end in the reference:
+it constructs its acoustic model as ``acousticModel(numMixtures, frameDim, fCorpus=..., tCorpus=..., ...)``
+(:86-92) but the shipped ``AudioHMMWordDiscoverer`` only accepts a corpus FILE (its matching constructor is
+the commented line audio_hmm_word_discoverer.py:15) -> TypeError.  Every numerical piece the class is made
+of DOES exist in the reference and is pinned by golden vectors generated from it:
   * segment cutting + resample embedding  : audio_segembed_hmm_word_discoverer.py:52-81,114-155
+    -> ``embed`` / ``sent_embeds`` == the reference's unbound ``embed`` / ``getSentEmbeds``
+       (tests/golden/seg_pieces.npz, made by tests/golden/make_golden_seg.py)
   * log-domain recursion / counts / Viterbi: audio_hmm_word_discoverer.py:148-254,396-427 with the
     emission hooks of its commented lines :157,:163,:180,:208,:403,:408 (obs_model.logTransProb)
-    -- this part IS pinned (same functions as oracle/plain_hmm.py, golden-tested)
-  * emission log N(x; mu, diag s2), mixture LSE : smt/audio_gmm_word_discoverer.py:53-61,395-401
+    -> same functions as oracle/plain_hmm.py, pinned by hmm_flickr24_log.npz / hmm_synth_log.npz
+  * emission log N(x; mu, diag s2), mixture LSE : smt/audio_gmm_word_discoverer.py:53-106,395-401
+    -> ``log_gauss`` / ``emission`` == the reference's ``gaussian(log_prob=True)`` / ``gmmProb(log_prob=True)``
   * mean update as posterior-weighted average   : smt/audio_gmm_word_discoverer.py:339-375
+    -> ``weighted_stats`` + ``means_from_stats`` == ``GMMWordDiscoverer.updateTranslationDensities``
+What has NO reference counterpart (design choices of the intended model, documented in DESIGN.md): how the
+pieces are wired together in ``em_iteration`` (posterior x within-state responsibility as the weight), the
+mixture-prior update for numMixtures > 1 and the optional variance update (the reference's GMM class resets
+its priors to 0 every M-step, :345-352, and its variance branch reads a stale normaliser, :378-383).
 """
 import math
 
@@ -95,33 +103,51 @@ def estep_pair(x, e, p):
     return dict(ll=logsumexp(a[-1]), init=init, trans=trans, post=post, resp=resp)
 
 
+def weighted_stats(embs, tgt, logw, Vt, M):
+    """Sufficient statistics of the Gaussian M-step: logw[u] is the (T, n, M) log weight of frame t for
+    (state j, mixture m) of utterance u.  Returns (w_sum (Vt, M), x_sum (Vt, M, D), xx_sum (Vt, M, D))."""
+    D = embs[0].shape[1]
+    w_sum = np.zeros((Vt, M))
+    x_sum = np.zeros((Vt, M, D))
+    xx_sum = np.zeros((Vt, M, D))
+    for x, e, lw in zip(embs, tgt, logw):
+        wgt = np.exp(lw)
+        for j, w in enumerate(e):
+            w_sum[w] += wgt[:, j].sum(0)
+            x_sum[w] += wgt[:, j].T @ x
+            xx_sum[w] += wgt[:, j].T @ (x ** 2)
+    return w_sum, x_sum, xx_sum
+
+
+def means_from_stats(old_means, w_sum, x_sum):
+    """updateTranslationDensities (:339-375): sum_t exp(logw - LSE(logw)) x_t == x_sum / w_sum; a (word,
+    mixture) that received no weight keeps its mean."""
+    means = old_means.copy()
+    with np.errstate(invalid='ignore', divide='ignore'):
+        mu = x_sum / w_sum[:, :, None]
+    ok = w_sum > 0
+    means[ok] = mu[ok]
+    return means, mu, ok
+
+
 def em_iteration(embs, tgt, p, acc, update_var=False):
     """One epoch.  acc: plain_hmm.LogAccumulators-like running init/trans accumulators (the
     reference's count lists live outside the epoch loop); the emission statistics are per epoch."""
     Vt, M, D = p['means'].shape
     lens = sorted(p['init'])
-    w_sum = np.zeros((Vt, M))
-    x_sum = np.zeros((Vt, M, D))
-    xx_sum = np.zeros((Vt, M, D))
+    logw = []
     for x, e in zip(embs, tgt):
         n = len(e)
         r = estep_pair(x, e, p)
         acc.init[n] = np.logaddexp(acc.init[n], r['init'])
         acc.trans[n] = np.logaddexp(acc.trans[n], r['trans'])
-        wgt = np.exp(r['post'][:, :, None] + r['resp'])          # (T, n, M)
-        for j, w in enumerate(e):
-            w_sum[w] += wgt[:, j].sum(0)
-            x_sum[w] += wgt[:, j].T @ x
-            xx_sum[w] += wgt[:, j].T @ (x ** 2)
+        logw.append(r['post'][:, :, None] + r['resp'])           # (T, n, M)
+    w_sum, x_sum, xx_sum = weighted_stats(embs, tgt, logw, Vt, M)
     new = dict(p)
     new['init'] = {m: acc.init[m] - logsumexp(acc.init[m]) for m in lens}
     new['trans'] = {m: acc.trans[m] - logsumexp(acc.trans[m], axis=1, keepdims=True) for m in lens}
     seen = w_sum.sum(1) > 0
-    means = p['means'].copy()
-    with np.errstate(invalid='ignore', divide='ignore'):
-        mu = x_sum / w_sum[:, :, None]
-    ok = w_sum > 0
-    means[ok] = mu[ok]
+    means, mu, ok = means_from_stats(p['means'], w_sum, x_sum)
     new['means'] = means
     lprior = p['lprior'].copy()
     if M > 1:

@@ -1,0 +1,21 @@
+"""Opt-in stand-in for `matplotlib` (see shim_stubs/_mwd_stub.py): defers to the real package when it is
+installed, otherwise installs an inert stub and warns on stderr."""
+import os
+import sys
+from unittest.mock import MagicMock
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+try:
+    import _mwd_stub
+finally:
+    sys.path.pop(0)
+
+# pyplot.subplots() is unpacked by the reference's plotting helpers (utils/plot.py:305,356)
+_REAL = _mwd_stub.activate(__name__, ('pyplot', 'colors', 'cm'), {'use': lambda *a, **k: None},
+                           {'pyplot': {'subplots': lambda *a, **k: (MagicMock(name='figure'), MagicMock(name='axes'))}})
+
+
+def __getattr__(name):
+    if name.startswith('__'):
+        raise AttributeError(name)
+    return MagicMock(name='matplotlib.' + name)

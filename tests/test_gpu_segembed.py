@@ -1,6 +1,8 @@
-"""Segment-embedding HMM (config 4): CUDA vs the restated oracle (oracle/segembed_hmm.py; the
-reference class is broken as shipped, so this row is pinned to the restatement, whose recursion /
-count / Viterbi parts are the golden-pinned functions of the log-domain class)."""
+"""Segment-embedding HMM (config 4): CUDA vs oracle/segembed_hmm.py.  The reference class cannot run end to
+end as shipped, so the oracle is pinned piece by piece to the reference code that exists -- gaussian() /
+gmmProb(), the GMM mean update, embed() (tests/test_oracle_seg_golden.py, tests/golden/seg_pieces.npz) and
+the log-domain recursion (hmm_*_log.npz) -- and the CUDA emission is also checked against those vectors
+directly (last test of this file)."""
 import numpy as np
 import pytest
 
@@ -111,3 +113,22 @@ def test_segembed_wrapper_end_to_end(tmp_path):
     ali = json.load(open(str(tmp_path / 'ali.json')))
     assert len(ali) == 12 and ali[0]['is_audio'] and ali[0]['image_concepts'][0] == 'NULL'
     assert len(ali[3]['alignment']) == int(lms['arr_3'][-1])          # one state index per frame
+
+
+def test_cuda_gaussian_emission_equals_reference_gmmprob():
+    """mwd_hmm_gauss_emission against vectors produced by the reference's own gaussian()/gmmProb()
+    (smt/audio_gmm_word_discoverer.py:53-106; tests/golden/seg_pieces.npz)."""
+    import os
+    from helpers import GOLDEN
+    from multimodalworddiscovery_b200.engine_hmm import SegmentHMMEngine
+    z = np.load(os.path.join(GOLDEN, 'seg_pieces.npz'))
+    x, means, var, lprior = z['g_x'], z['g_means'], z['g_var'], z['g_lprior']
+    M = means.shape[0]
+    eng = SegmentHMMEngine([np.array([0])], [x], 1, M, emb_dtype=np.float64)
+    eng.set_chain_params({1: np.zeros(1)}, {1: np.zeros((1, 1))})
+    eng.set_emission_params(lprior[None], means[None], var[None])
+    eng.emission()
+    np.testing.assert_allclose(eng.emis.cpu().numpy()[:x.shape[0]], z['g_gmm'], rtol=1e-12, atol=1e-10)
+    eng.set_emission_params(lprior[None], means[None], 0.02 * np.ones((1, M, x.shape[1])))
+    eng.emission()
+    np.testing.assert_allclose(eng.emis.cpu().numpy()[:x.shape[0]], z['g_gmm_fixedvar'], rtol=1e-12, atol=1e-8)
