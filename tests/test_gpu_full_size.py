@@ -10,6 +10,13 @@ hmm_dnn/image_phone_hmm_word_discoverer.py:355, :396, :462-465, :529):
   * log(EPS) <= per-pair log-likelihood <= 0;
   * the counts of the whole corpus equal the fixed-order sum of the counts of its two halves
     (the data-parallel sharding of DESIGN.md section 6 -- pairs are independent inside an E-step).
+
+Also at full size: the fused concept_alignment output equals the argmax of a materialised conceptCountsA for
+every one of the ~50 M phones; Viterbi align + cluster run over all pairs and equal the oracle bit for bit on a
+2 000-pair sub-corpus; and the count tables (translation, initial, transition), log-likelihood and
+concept_alignment of that sub-corpus, computed by the same kernels at the full-size shapes (D = 512, K = 65 /
+100), equal the oracle's to 1e-9.  Variants: MSCOCO shape linear (configs[4]) and Gaussian (configs[1] shape),
+Flickr30k shape (configs[2] shape: K = 100, P = 69, n ~ 1..8, Toeplitz pooling on).
 """
 import os
 import sys
@@ -27,14 +34,123 @@ N_PAIRS = int(os.environ.get('MWD_FULL_SIZE_PAIRS', '1000000'))
 NMAX = 16
 
 
-def _shard(torch, dev, rank, world):
+def _shard(torch, dev, rank, world, variant='coco5', gaussian=False):
     import bench
     from multimodalworddiscovery_b200.corpus import pack_sorted_arrays
-    sh = bench.make_shard(torch, dev, N_PAIRS, rank, world, 'coco5')
+    bench.apply_variant(variant)
+    sh = bench.make_shard(torch, dev, N_PAIRS, rank, world, variant)
     pk = pack_sorted_arrays(sh['region_off'].cpu().numpy(), sh['phone_off'].cpu().numpy(),
                             sh['feats'].cpu().numpy(), sh['phones'].cpu().numpy(), lens=sh['lens'],
                             n_pairs_global=N_PAIRS)
-    return pk, sh['W'].cpu().numpy()
+    return pk, (sh['mus'] if gaussian else sh['W']).cpu().numpy()
+
+
+def _sub_corpus(pk, pos):
+    """The pairs at sorted positions ``pos`` (ascending) of a packed shard as (feats list, phones list)."""
+    feats = [np.asarray(pk.feats[int(pk.region_off[s]):int(pk.region_off[s + 1])], dtype=np.float64) for s in pos]
+    phones = [np.asarray(pk.phones[int(pk.phone_off[s]):int(pk.phone_off[s + 1])]) for s in pos]
+    return feats, phones
+
+
+def _near_tie(values, a, b, rel=1e-12):
+    return abs(values[a] - values[b]) <= rel * max(abs(values[a]), abs(values[b]))
+
+
+@pytest.mark.parametrize('variant,gaussian', [('coco5', False), ('coco5', True), ('flickr', False)])
+def test_full_size_decode_and_subcorpus_tables(variant, gaussian):
+    """Satisfies what the north star calls bit-exact AT the full size, plus a 2 000-pair oracle comparison of
+    the count tables produced by the full-size kernel shapes."""
+    import torch
+    import bench
+    from oracle import image_phone_hmm as orc
+    from multimodalworddiscovery_b200.corpus import pack_pairs
+    from multimodalworddiscovery_b200.engine import IKEngine
+    dev = torch.device('cuda', 0)
+    pk, post = _shard(torch, dev, 0, 1, variant, gaussian)
+    K, P, D = bench.K_CONCEPTS, bench.P_PHONES, bench.D_FEAT
+    kind = 'gaussian' if gaussian else 'linear'
+    width = float(D) if gaussian else 1.0
+    init, trans, obs = _params(K, P, pk.lens)
+    eng = IKEngine(pk, K, P, gaussian=gaussian, device=dev)
+    eng.set_params(init, trans, obs, post)
+    eng._snapshot_entering(width)
+    eng.estep(width, with_cA=False)
+    # fused concept_alignment == argmax of the materialised conceptCountsA, every phone of the corpus
+    fused = eng.concept_alignment().cpu().numpy().copy()
+    dense = eng.concept_alignment_from_cA().cpu().numpy()
+    assert np.array_equal(fused, dense)
+    eng.cA = None
+    torch.cuda.empty_cache()
+    # Viterbi + cluster over the whole corpus
+    ali, ic, _ = eng.decode(floor_norm=gaussian, want_probs=False, width=width)
+    ali, ic = ali.cpu().numpy(), ic.cpu().numpy()
+    n_of = np.repeat(np.diff(pk.region_off), np.diff(pk.phone_off))
+    assert ali.min() >= 0 and np.all(ali < n_of) and ic.min() >= 0 and ic.max() < K
+    ll_full = eng.pair_ll[:pk.n_pairs].cpu().numpy()
+
+    # ---- 2 000-pair sub-corpus against the oracle
+    rng = np.random.default_rng(5)
+    n_sub = min(2000, pk.n_pairs)
+    pos = np.sort(rng.choice(pk.n_pairs, n_sub, replace=False))
+    feats, phones = _sub_corpus(pk, pos)
+    oparams = dict(init=init, trans=trans, obs=obs, lr=0.1, momentum=0.0, toeplitz=len(pk.lens) >= 6)
+    if gaussian:
+        oparams.update(mus=post, width=width)
+    else:
+        oparams['W'] = post
+    new, info = orc.em_iteration(feats, phones, oparams, kind)
+    A_of = {m: np.asarray(trans[m]) for m in pk.lens}
+    mism_ali = mism_ic = mism_ca = 0
+    for q, s in enumerate(pos):
+        p0, p1 = int(pk.phone_off[s]), int(pk.phone_off[s + 1])
+        r0, r1 = int(pk.region_off[s]), int(pk.region_off[s + 1])
+        n = r1 - r0
+        pz = info['pz'][q]
+        path, _ = orc.align(pz, phones[q], obs, np.asarray(init[n]), A_of[n], floor_norm=gaussian)
+        if ali[p0:p1].tolist() != path:
+            mism_ali += 1
+        concepts, scores = orc.cluster(pz, phones[q], obs, path)
+        for i in range(n):
+            if ic[r0 + i] != concepts[i]:
+                assert _near_tie(scores[i], ic[r0 + i], concepts[i]), (s, i)
+                mism_ic += 1
+        ca_ref = np.argmax(info['cA'][q], axis=1)
+        for t in np.flatnonzero(ca_ref != fused[p0:p1]):
+            assert _near_tie(info['cA'][q][t], ca_ref[t], fused[p0 + t]), (s, t)
+            mism_ca += 1
+    assert mism_ali == 0, 'Viterbi paths differ from the oracle on %d of %d pairs' % (mism_ali, n_sub)
+    assert mism_ic == 0 and mism_ca == 0, (mism_ic, mism_ca)
+    # per-pair log-likelihood of the sub-corpus, taken from the FULL-size run
+    ll_sub = np.array([orc.pair_loglik(orc.forward(info['pz'][q], phones[q], obs, np.asarray(init[len(feats[q])]),
+                                                   A_of[len(feats[q])])) for q in range(0, n_sub, 8)])
+    np.testing.assert_allclose(ll_full[pos[::8]], ll_sub, rtol=1e-9)
+    del eng
+    torch.cuda.empty_cache()
+    # count tables of the sub-corpus through the same kernels (full-size D / K / P shapes)
+    pks = pack_pairs(feats, phones, feat_dtype=np.float32)
+    e2 = IKEngine(pks, K, P, gaussian=gaussian, device=dev)
+    e2.toeplitz = 1 if oparams['toeplitz'] else 0
+    e2.set_params(init, trans, obs, post)
+    e2.estep(width, with_cA=False)
+    counts = e2.counts.cpu().numpy()
+    pe, ie, te = P * K, (NMAX + 1) * NMAX, (NMAX + 1) * NMAX * NMAX
+    np.testing.assert_allclose(counts[:pe].reshape(P, K).T, info['phoneC'], rtol=1e-9, atol=1e-300)
+    initC = counts[pe:pe + ie].reshape(NMAX + 1, NMAX)
+    transC = counts[pe + ie:pe + ie + te].reshape(NMAX + 1, NMAX * NMAX)
+    for m in pks.lens:
+        np.testing.assert_allclose(initC[m][:m], info['initC'][m], rtol=1e-9)
+        raw = transC[m][:m * m].reshape(m, m)            # the kernels pool along diagonals once, in the M-step
+        np.testing.assert_allclose(orc.toeplitz_pool(raw) if oparams['toeplitz'] else raw, info['transC'][m], rtol=1e-9)
+    np.testing.assert_allclose(counts[pe + ie + te], info['avg_ll'] * n_sub, rtol=1e-9)
+    # one whole EM iteration of the sub-corpus: updated tables vs the oracle's M-step
+    e2.allreduce()
+    e2.mstep(0.1, 0.0, width)
+    i2, t2, o2, p2 = e2.get_params()
+    for m in pks.lens:
+        np.testing.assert_allclose(i2[m], new['init'][m], rtol=1e-9)
+        np.testing.assert_allclose(t2[m], new['trans'][m], rtol=1e-9)
+    np.testing.assert_allclose(o2, new['obs'], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(p2, new['mus' if gaussian else 'W'], rtol=1e-8, atol=1e-12)
 
 
 def _params(K, P, lens, seed=7):

@@ -131,3 +131,35 @@ def test_twolayer_class_matches_reference(case, tmp_path):
     h0 = m.hiddenLayer(v0)
     assert h0.shape == (v0.shape[0], m.hiddenDim) and np.all(h0 >= 0)
     np.testing.assert_allclose(m.softmaxLayer(h0).sum(1), 1.0, rtol=1e-12)
+
+
+def test_default_feature_dtype_keeps_float64_inputs_exact(tmp_path):
+    """Default config (no feature_dtype key), normalize_vfeat=True: the normalised features are not float32
+    values, so the class must keep them in float64 -- tables to 1e-9 and bit-exact Viterbi paths against the
+    oracle run on the SAME float64 features (reference :54-55 normalises in float64)."""
+    from oracle import image_phone_hmm as orc
+    from helpers import write_ik_files
+    from multimodalworddiscovery_b200.corpus import resolve_feature_dtype
+    from multimodalworddiscovery_b200.hmm_dnn.image_phone_hmm_word_discoverer import ImagePhoneHMMWordDiscoverer
+    g = load_ik('mixed_linear')
+    tmp = str(tmp_path)
+    caps, feats, cfg, extra = write_ik_files(tmp, g)
+    cfg.pop('feature_dtype')
+    cfg['normalize_vfeat'] = True
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ImagePhoneHMMWordDiscoverer(caps, feats, cfg, obsProbFile=extra.get('obs'), modelName=os.path.join(tmp, 'm'))
+        m.trainUsingEM(2, printStatus=True)
+        m.printAlignment(os.path.join(tmp, 'ali'))
+    assert m._eng.feat_is_f64 == 1
+    assert resolve_feature_dtype('auto', g['feats_list']) == np.float32      # the un-normalised fixtures ARE float32 values
+    vn = [(v.T / np.linalg.norm(v, ord=2, axis=-1)).T for v in g['feats_list']]
+    p = orc.initial_params(vn, g['K'], g['P'], 'linear', W=g['param0'], lr=g['lr'], momentum=g['momentum'], obs=g.get('obs0'))
+    for _ in range(2):
+        p, info = orc.em_iteration(vn, g['phones_list'], p, 'linear')
+    np.testing.assert_allclose(m.obs, p['obs'], rtol=RTOL, atol=1e-300)
+    np.testing.assert_allclose(m.W, p['W'], rtol=1e-8, atol=1e-12)
+    ali = json.load(open(os.path.join(tmp, 'ali.json')))
+    for ex, (v, x) in enumerate(zip(vn, g['phones_list'])):
+        n = v.shape[0]
+        path, _ = orc.align(orc.posterior_linear(v, p['W']), x, p['obs'], p['init'][n], p['trans'][n])
+        assert ali[ex]['alignment'] == path
