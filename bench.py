@@ -321,7 +321,8 @@ def gpu_arm(args):
     torch.cuda.empty_cache()
     gaussian = args.model == 'gaussian'
     width = float(D_FEAT) if gaussian else 1.0       # RBF width of the order of |v - mu|^2 (unit-variance noise)
-    eng = IKEngine(pk, K_CONCEPTS, P_PHONES, gaussian=gaussian, device=dev, keep_concept_counts_a=False)
+    eng = IKEngine(pk, K_CONCEPTS, P_PHONES, gaussian=gaussian, device=dev, keep_concept_counts_a=False,
+                   mixed_precision=args.mixed)
     if args.chunks <= 0:
         # enough chunks to overlap the PCIe copy with the kernels, not so many that a small corpus
         # drowns in launches (1 M pairs: 10.4 GB -> 16 chunks; MSCOCO-2k: 21 MB -> 1 chunk)
@@ -494,6 +495,8 @@ def main():
     ap.add_argument('--model', default='linear', choices=['linear', 'gaussian'],
                     help="image posterior: linear softmax (default, BASELINE configs[0]/[4]) or RBF (configs[1]); "
                          "the CPU arm always times the linear class")
+    ap.add_argument('--mixed', default='float64',
+                    help="precision of the floor-free parts: 'float64' (reference arithmetic) | 'mixed' | subset like 'concept+posterior'")
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunks', type=int, default=0,

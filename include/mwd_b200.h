@@ -43,6 +43,9 @@ extern "C" {
 #define MWD_NMAX 16          /* max regions (HMM states) per image                       */
 #define MWD_KMAX 128         /* max concepts (nWords)                                     */
 #define MWD_EPS 1e-50        /* hmm_dnn/image_phone_hmm_word_discoverer.py:11             */
+#define MWD_MIXED_CONCEPT 1
+#define MWD_MIXED_POSTERIOR 2
+#define MWD_MIXED_GRAD 4
 #define MWD_INIT_STRIDE MWD_NMAX
 #define MWD_TRANS_STRIDE (MWD_NMAX * MWD_NMAX)
 
@@ -104,7 +107,14 @@ typedef struct {
                                 normalisers of ImageAudioGaussianHMMWordDiscoverer
                                 (image_audio_gaussian_hmm_word_discoverer.py:369-371,414-415,449-451,
                                 :629-631): likelihood, gamma and xi are divided by their raw sums   */
-  int32_t reserved0;
+  int32_t mixed_precision;   /* 0: everything in float64, bit for bit the reference's arithmetic class (default).
+                                Bits (MWD_MIXED_*) move the parts of the iteration that have NO EPS floor
+                                off the FP64 pipe; they are validated against the float64 path at the
+                                north-star tolerance (1e-5 on log-likelihood and tables), never bit-exact:
+                                  MWD_MIXED_CONCEPT    updateConceptCounts chains in float32 (FFMA pipe)
+                                  MWD_MIXED_POSTERIOR  softmaxLayer GEMM on tcgen05 int8 slices (exact
+                                                       integer products, float64 recombination)
+                                  MWD_MIXED_GRAD       updateSoftmaxWeight GEMM likewise             */
   int32_t* concept_alignment;/* [dev] Ttot or NULL: argmax_k conceptCountsA[t][k] (first index on ties, the
                                 `concept_alignment` of printAlignment :628) written by mwd_ik_estep from
                                 the column sums it forms anyway -- 4 bytes per phone instead of the

@@ -16,8 +16,27 @@ TRANS_STRIDE = NMAX * NMAX
 EPS = 1e-50
 
 
+MIXED_CONCEPT, MIXED_POSTERIOR, MIXED_GRAD = 1, 2, 4
+
+
 class MwdError(RuntimeError):
     pass
+
+
+def mixed_bits(spec):
+    """modelConfigs['posterior_precision'] / engine ``mixed_precision`` -> MWD_MIXED_* bits.
+    'float64' | None | 0: reference arithmetic everywhere (default); 'mixed': every floor-free part of the
+    iteration off the FP64 pipe; or an explicit int / '+'-joined subset of 'concept', 'posterior', 'grad'."""
+    if spec is None or spec is False or spec == 0 or spec == 'float64':
+        return 0
+    if spec is True or spec == 'mixed':
+        return MIXED_CONCEPT | MIXED_POSTERIOR | MIXED_GRAD
+    if isinstance(spec, int):
+        return spec & 7
+    bits = 0
+    for part in str(spec).split('+'):
+        bits |= {'concept': MIXED_CONCEPT, 'posterior': MIXED_POSTERIOR, 'grad': MIXED_GRAD}[part.strip()]
+    return bits
 
 
 class Geometry(C.Structure):
@@ -37,7 +56,7 @@ class IkProblem(C.Structure):
         ('pair_ll', C.c_void_p), ('concept_counts_a', C.c_void_p),
         ('part_phone', C.c_void_p), ('part_init', C.c_void_p), ('part_trans', C.c_void_p),
         ('scratch', C.c_void_p), ('scratch_bytes', C.c_int64),
-        ('stats', C.c_void_p), ('slot_off', C.c_void_p), ('no_floor', C.c_int32), ('reserved0', C.c_int32),
+        ('stats', C.c_void_p), ('slot_off', C.c_void_p), ('no_floor', C.c_int32), ('mixed_precision', C.c_int32),
         ('concept_alignment', C.c_void_p),
     ]
 

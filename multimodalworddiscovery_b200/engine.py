@@ -26,7 +26,7 @@ class IKEngine(object):
     """Holds one rank's packed shard, the model parameters and all workspaces in HBM."""
 
     def __init__(self, packed, n_concepts, n_phone_types, gaussian=False, device=None,
-                 keep_concept_counts_a=False, process_group=None, hidden_dim=0):
+                 keep_concept_counts_a=False, process_group=None, hidden_dim=0, mixed_precision=0):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -41,6 +41,8 @@ class IKEngine(object):
         if not (1 <= self.K <= _lib.KMAX):
             raise ValueError('n_words=%d outside [1,%d]' % (self.K, _lib.KMAX))
         self.gaussian = bool(gaussian)
+        # MWD_MIXED_* bits (include/mwd_b200.h): 0 = float64 everywhere (reference arithmetic, default)
+        self.mixed = _lib.mixed_bits(mixed_precision)
         self.H = int(hidden_dim)              # > 0: two-layer (ReLU MLP) image posterior
         self.two_layer = self.H > 0
         self.D = int(packed.feats.shape[1])
@@ -145,6 +147,7 @@ class IKEngine(object):
         p.pair_ll = _ptr(self.pair_ll)
         p.concept_counts_a = _ptr(self.cA) if (with_cA and self.cA is not None) else C.c_void_p(0)
         p.concept_alignment = _ptr(self.ca)
+        p.mixed_precision = self.mixed
         p.part_phone, p.part_init = _ptr(self._part_phone), _ptr(self._part_init)
         p.part_trans = _ptr(self._part_trans)
         p.scratch = _ptr(self.scratch)

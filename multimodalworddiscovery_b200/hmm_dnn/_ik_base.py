@@ -196,7 +196,8 @@ class ImagePhoneHMMBase(object):
             pk = pack_pairs(self.vCorpus, self._phone_ids(), feat_dtype=dt, rank=rank, world=world)
             self._eng = IKEngine(pk, self.nWords, self.audioFeatDim, gaussian=self.GAUSSIAN,
                                  device=self._device, keep_concept_counts_a=self._keep_cA,
-                                 hidden_dim=(self.hiddenDim if self.TWO_LAYER else 0))
+                                 hidden_dim=(self.hiddenDim if self.TWO_LAYER else 0),
+                                 mixed_precision=getattr(self, '_posterior_precision', 0))
             self._eng_token = token
             self._cA_valid = False
         return self._eng

@@ -35,6 +35,7 @@ class ImagePhoneGaussianHMMWordDiscoverer(ImagePhoneHMMBase):
     self.normalize_vfeat = modelConfigs.get('normalize_vfeat', False)   # read but ignored, as in the reference
     self._device = modelConfigs.get('device', None)
     self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
+    self._posterior_precision = modelConfigs.get('posterior_precision', 'float64')   # or 'mixed' (see _lib.mixed_bits)
     self._keep_cA = modelConfigs.get('keep_concept_counts_a', False)   # conceptCountsA is materialised on access
     # The reference silently keeps only the first 30 pairs (debug leftover, :56,:87).  Default is
     # bug-compatible; set modelConfigs['max_pairs']=None to train on the whole corpus.

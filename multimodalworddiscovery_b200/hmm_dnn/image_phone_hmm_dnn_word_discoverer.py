@@ -36,6 +36,7 @@ class ImagePhoneHMMDNNWordDiscoverer(ImagePhoneHMMBase):
     self.normalize_vfeat = modelConfigs.get('normalize_vfeat', False)
     self._device = modelConfigs.get('device', None)
     self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
+    self._posterior_precision = modelConfigs.get('posterior_precision', 'float64')   # or 'mixed' (see _lib.mixed_bits)
     self._keep_cA = False                      # the reference class keeps no conceptCountsA
 
     self.init = {}

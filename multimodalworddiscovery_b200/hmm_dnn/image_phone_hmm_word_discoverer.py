@@ -39,6 +39,7 @@ class ImagePhoneHMMWordDiscoverer(ImagePhoneHMMBase):
     # optional, B200-build-only keys (defaults keep unchanged drivers working)
     self._device = modelConfigs.get('device', None)
     self._feature_dtype = modelConfigs.get('feature_dtype', 'auto')
+    self._posterior_precision = modelConfigs.get('posterior_precision', 'float64')   # or 'mixed' (see _lib.mixed_bits)
     self._keep_cA = modelConfigs.get('keep_concept_counts_a', False)   # conceptCountsA is materialised on access
 
     self.init = {}

@@ -1,0 +1,100 @@
+"""The opt-in mixed-precision path (modelConfigs['posterior_precision'] = 'mixed', mwd_ik_problem.mixed_precision)
+against the float64 path of the same library at the NORTH-STAR tolerance: 1e-5 relative on log-likelihood and
+every table over 20 EM iterations; Viterbi / cluster outputs come from the float64 decode kernel in both modes
+and must be identical whenever the tables are.  The parts that move off the FP64 pipe are exactly those with no
+EPS floor (SURVEY 8a census): softmaxLayer, updateConceptCounts, updateSoftmaxWeight."""
+import numpy as np
+import pytest
+
+from helpers import flatten_tables, load_ik, oracle_params_from_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _engine(feats, phones, K, P, gaussian, mixed, dtype=np.float32):
+    from multimodalworddiscovery_b200.corpus import pack_pairs
+    from multimodalworddiscovery_b200.engine import IKEngine
+    pk = pack_pairs(feats, phones, feat_dtype=dtype)
+    return IKEngine(pk, K, P, gaussian=gaussian, mixed_precision=mixed)
+
+
+def _synth(rng, N, K, P, D, n_choices, T_lo, T_hi, scale=10.0):
+    cent = scale * rng.standard_normal((K, D))
+    pw = 1.0 / np.arange(1, P + 1) ** 1.2
+    pw /= pw.sum()
+    feats, phones = [], []
+    for _ in range(N):
+        n = int(rng.choice(n_choices))
+        feats.append((cent[rng.integers(0, K, n)] + rng.standard_normal((n, D))).astype(np.float32).astype(np.float64))
+        phones.append(rng.choice(P, size=int(rng.integers(T_lo, T_hi + 1)), p=pw).astype(np.int32))
+    return feats, phones, cent
+
+
+@pytest.mark.parametrize('case', ['mixed_linear', 'long_floor_linear', 'short_toeplitz_linear', 'mixed_gaussian'])
+def test_concept_chains_float32_vs_float64_on_goldens(case):
+    g = load_ik(case)
+    p = oracle_params_from_golden(g)
+    gaussian = g['kind'] == 'gaussian'
+    out = []
+    for mixed in (0, 'concept'):
+        eng = _engine(g['feats_list'], g['phones_list'], g['K'], g['P'], gaussian, mixed, np.float64)
+        eng.set_params(p['init'], p['trans'], p['obs'], p['mus'] if gaussian else p['W'])
+        eng.estep(g['width'])
+        out.append(eng.cC[:eng.pk.n_regions].cpu().numpy().copy())
+    np.testing.assert_allclose(out[1], out[0], rtol=TOL, atol=1e-12)
+    np.testing.assert_allclose(out[1].sum(1), 1.0, rtol=1e-12)
+
+
+@pytest.mark.parametrize('K,n_choices', [(65, [5]), (65, list(range(1, 11))), (100, [1, 2, 3, 4, 5, 6, 7, 8]), (40, [3, 9, 12])])
+def test_concept_chains_float32_full_shapes(K, n_choices):
+    rng = np.random.default_rng(K + len(n_choices))
+    P, D = 49, 64
+    feats, phones, _ = _synth(rng, 120, K, P, D, n_choices, 15, 125, scale=1.0)
+    W = 0.1 * rng.standard_normal((K, D + 1))
+    lens = sorted({v.shape[0] for v in feats})
+    init = {m: (lambda v: v / v.sum())(rng.random(m) + 0.5) for m in lens}
+    trans = {m: (lambda v: v / v.sum(1, keepdims=True))(rng.random((m, m)) + 0.5) for m in lens}
+    obs = rng.random((K, P)) ** 6 + 1e-9                       # peaky rows: six orders of magnitude inside a row
+    obs /= obs.sum(1, keepdims=True)
+    out = []
+    for mixed in (0, 'concept'):
+        eng = _engine(feats, phones, K, P, False, mixed)
+        eng.set_params(init, trans, obs, W)
+        eng.estep(1.0)
+        out.append(eng.cC[:eng.pk.n_regions].cpu().numpy().copy())
+    np.testing.assert_allclose(out[1], out[0], rtol=TOL, atol=1e-12)
+
+
+@pytest.mark.parametrize('gaussian', [False, True])
+def test_twenty_em_iterations_mixed_vs_float64(gaussian):
+    """Acceptance gate of the mixed path: 20 iterations from the same start, LL and every table to 1e-5."""
+    rng = np.random.default_rng(3 if gaussian else 2)
+    K, P, D = 65, 49, 512
+    feats, phones, cent = _synth(rng, 1500, K, P, D, [5], 15, 90)
+    post = (cent + 0.5 * rng.standard_normal((K, D))) if gaussian else 0.01 * rng.standard_normal((K, D + 1))
+    width = float(D) if gaussian else 1.0
+    lens = [5]
+    init = {5: np.ones(5) / 5}
+    trans = {5: np.ones((5, 5)) / 5}
+    obs = np.ones((K, P)) / P
+    engs = []
+    for mixed in (0, 'mixed'):
+        eng = _engine(feats, phones, K, P, gaussian, mixed)
+        eng.set_params(init, trans, obs, post)
+        engs.append(eng)
+    lr = 0.1
+    for it in range(20):
+        lls = [float(e.em_iteration(lr, 0.0, width)) for e in engs]
+        np.testing.assert_allclose(lls[1], lls[0], rtol=TOL, err_msg='iteration %d' % it)
+        a, b = engs[0].get_params(), engs[1].get_params()
+        np.testing.assert_allclose(flatten_tables(lens, b[0]), flatten_tables(lens, a[0]), rtol=TOL, err_msg='init %d' % it)
+        np.testing.assert_allclose(flatten_tables(lens, b[1]), flatten_tables(lens, a[1]), rtol=TOL, err_msg='trans %d' % it)
+        np.testing.assert_allclose(b[2], a[2], rtol=TOL, atol=1e-300, err_msg='obs %d' % it)
+        np.testing.assert_allclose(b[3], a[3], rtol=TOL, atol=1e-9, err_msg='posterior parameter %d' % it)
+        if (it + 1) % 10 == 0:
+            lr /= 10
+    # decode runs the float64 kernels in both modes: identical tables up to 1e-5 must give (near-)identical paths
+    d0, d1 = engs[0].decode(floor_norm=gaussian, want_probs=False, width=width), engs[1].decode(floor_norm=gaussian, want_probs=False, width=width)
+    same = (d0[0] == d1[0]).float().mean().item()
+    assert same > 0.999, same
