@@ -213,8 +213,8 @@ def test_full_size_properties_and_oracle_spot_checks():
     import bench
     from oracle import image_phone_hmm as orc
     dev = torch.device('cuda', 0)
-    K, P = bench.K_CONCEPTS, bench.P_PHONES
     pk, eng, params = _run(torch, dev, 0, 1)
+    K, P = bench.K_CONCEPTS, bench.P_PHONES          # after _run: _shard() re-applies the coco5 variant
     counts = eng.counts.cpu().numpy()
     pe, ie, te = P * K, (NMAX + 1) * NMAX, (NMAX + 1) * NMAX * NMAX
     initC = counts[pe:pe + ie].reshape(NMAX + 1, NMAX)
