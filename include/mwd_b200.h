@@ -112,9 +112,11 @@ typedef struct {
                                 off the FP64 pipe; they are validated against the float64 path at the
                                 north-star tolerance (1e-5 on log-likelihood and tables), never bit-exact:
                                   MWD_MIXED_CONCEPT    updateConceptCounts chains in float32 (FFMA pipe)
-                                  MWD_MIXED_POSTERIOR  softmaxLayer GEMM on tcgen05 int8 slices (exact
-                                                       integer products, float64 recombination)
-                                  MWD_MIXED_GRAD       updateSoftmaxWeight GEMM likewise             */
+                                  MWD_MIXED_POSTERIOR  softmaxLayer GEMM on tcgen05 (kind::tf32, operands split
+                                                       hi + lo, fp32 TMEM accumulators, float64 recombination
+                                                       + softmax), features through TMA; linear class, fp32
+                                                       features (mwd_posterior_linear_tc)
+                                  MWD_MIXED_GRAD       updateSoftmaxWeight GEMM likewise (mwd_ik_posterior_grad_tc) */
   int32_t* concept_alignment;/* [dev] Ttot or NULL: argmax_k conceptCountsA[t][k] (first index on ties, the
                                 `concept_alignment` of printAlignment :628) written by mwd_ik_estep from
                                 the column sums it forms anyway -- 4 bytes per phone instead of the
@@ -128,6 +130,34 @@ int64_t mwd_ik_scratch_bytes(const mwd_ik_problem* p);
  *   pz[r][k] = softmax_k( feats[r] . W[k][0:D] + W[k][D] )                                  */
 int mwd_posterior_linear(const void* feats, int feat_is_f64, int64_t n_regions, int feat_dim,
                          const double* W, int n_concepts, double* pz, void* stream);
+
+/* softmaxLayer on the Blackwell tensor cores (tcgen05.mma kind::tf32 + TMA + TMEM), the MWD_MIXED_POSTERIOR path:
+ * same result contract as mwd_posterior_linear to ~1e-6 relative (split-TF32 operands, see csrc/posterior_tc.cu);
+ * fp32 features only.  w_split_scratch [dev]: mwd_posterior_tc_scratch_bytes(K, D) bytes, 16-byte aligned.
+ * split_mode 0: both feature parts rounded to TF32 in shared memory; 1: the high part is the raw fp32 word
+ * (relies on the tensor core ignoring the low 13 mantissa bits).  mwd_posterior_tc_supported() tells whether a
+ * shape can take this path (fp32 features, D % 4 == 0, D >= 32, K <= MWD_KMAX).                              */
+int64_t mwd_posterior_tc_scratch_bytes(int n_concepts, int feat_dim);
+int mwd_posterior_tc_supported(int feat_is_f64, int feat_dim, int n_concepts);
+int mwd_posterior_linear_tc(const float* feats, int64_t n_regions, int feat_dim, const double* W,
+                            int n_concepts, double* pz, void* w_split_scratch, int split_mode, void* stream);
+
+/* updateSoftmaxWeight GEMM on the Blackwell tensor cores, the MWD_MIXED_GRAD path (csrc/posterior_grad_tc.cu):
+ *   grad[k][d] = sum_r (concept_counts - pz)[r][k] * [feats,1][r][d]   -- image_phone_hmm_word_discoverer.py:475-488
+ * split-TF32 operands, fp32 TMEM accumulation over at most 2048 rows, float64 per-CTA partial tables summed in fixed
+ * order (deterministic).  partials [dev]: mwd_posterior_grad_tc_partials_len(K, D) doubles.  _partial with
+ * accumulate == 0 zeroes the partial tables first; accumulate != 0 adds another chunk of the shard.  _finish writes
+ * grad (K x (D+1)).  Uses p->feats (fp32), p->concept_counts, p->pz, p->n_regions, p->feat_dim, p->n_concepts.     */
+int mwd_posterior_grad_tc_supported(int feat_is_f64, int feat_dim, int n_concepts);
+int64_t mwd_posterior_grad_tc_partials_len(int n_concepts, int feat_dim);
+int mwd_ik_posterior_grad_tc_partial(const mwd_ik_problem* p, double* partials, int accumulate, int split_mode,
+                                     void* stream);
+int mwd_posterior_grad_tc_finish(int n_concepts, int feat_dim, const double* partials, double* grad, void* stream);
+
+/* Diagnostic (tools/umma_layout_probe.py): n_mma tcgen05.mma kind::tf32 on caller-supplied shared-memory images and
+ * matrix descriptors (start-address field zero), the 128 x n_cols fp32 accumulator dumped to out.                */
+int mwd_umma_probe(const void* a_img, int a_words, const void* b_img, int b_words, uint64_t adesc, uint64_t bdesc,
+                   uint32_t idesc, int n_cols, int n_mma, uint32_t a_step, uint32_t b_step, float* out, void* stream);
 
 /* softmaxLayer -- image_phone_gaussian_hmm_word_discoverer.py:501-510:
  *   pz[r][k] = softmax_k( -||feats[r] - mus[k]||^2 / width )

@@ -109,6 +109,14 @@ SYMBOLS = {
     'mwd_get_geometry': (_i, [C.POINTER(Geometry)]),
     'mwd_ik_scratch_bytes': (_i64, [C.POINTER(IkProblem)]),
     'mwd_posterior_linear': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp, _vp]),
+    'mwd_posterior_tc_scratch_bytes': (_i64, [_i, _i]),
+    'mwd_posterior_tc_supported': (_i, [_i, _i, _i]),
+    'mwd_posterior_linear_tc': (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    'mwd_posterior_grad_tc_supported': (_i, [_i, _i, _i]),
+    'mwd_posterior_grad_tc_partials_len': (_i64, [_i, _i]),
+    'mwd_ik_posterior_grad_tc_partial': (_i, [C.POINTER(IkProblem), _vp, _i, _i, _vp]),
+    'mwd_posterior_grad_tc_finish': (_i, [_i, _i, _vp, _vp, _vp]),
+    'mwd_umma_probe': (_i, [_vp, _i, _vp, _i, C.c_uint64, C.c_uint64, C.c_uint32, _i, _i, C.c_uint32, C.c_uint32, _vp, _vp]),
     'mwd_posterior_gaussian': (_i, [_vp, _i, _i64, _i, _vp, _d, _i, _vp, _vp, _vp]),
     'mwd_hidden_relu': (_i, [_vp, _i, _i64, _i, _vp, _i, _vp, _vp]),
     'mwd_backprop_hidden': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),

@@ -5,6 +5,7 @@ kernel of libmwd_b200.so called through the C ABI of include/mwd_b200.h.  There 
 fallback: without a CUDA device or without the built library, construction raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -109,6 +110,11 @@ class IKEngine(object):
         if self.two_layer:
             gp_len = max(gp_len, int(self.lib.mwd_outer_grad_partials_len(self.K, self.H)),
                          int(self.lib.mwd_outer_grad_partials_len(self.H, self.D)))
+        # tensor-core (tcgen05) gradient GEMM: opt-in (MWD_MIXED_GRAD), fp32 features, not the two-layer class
+        self._tc_grad = bool(self.mixed & _lib.MIXED_GRAD) and not self.two_layer \
+            and bool(self.lib.mwd_posterior_grad_tc_supported(self.feat_is_f64, self.D, self.K))
+        if self._tc_grad:
+            gp_len = max(gp_len, int(self.lib.mwd_posterior_grad_tc_partials_len(self.K, self.D)))
         self.grad_partials = torch.empty((gp_len,), dtype=f64, device=dev)
         self._lens = np.ascontiguousarray(np.array(packed.lens, dtype=np.int32))
         self.toeplitz = 1 if len(packed.lens) >= 6 else 0     # :399
@@ -123,6 +129,13 @@ class IKEngine(object):
         need = int(self.lib.mwd_ik_scratch_bytes(C.byref(prob)))
         self.scratch = torch.empty((max(need, 8) // 8 + 1,), dtype=f64, device=dev)
         self.last_counts = None
+        # tensor-core (tcgen05) posterior of the linear class: opt-in, fp32 features only
+        self._tc_posterior = bool(self.mixed & _lib.MIXED_POSTERIOR) and not self.gaussian and not self.two_layer \
+            and bool(self.lib.mwd_posterior_tc_supported(self.feat_is_f64, self.D, self.K))
+        self._tc_split_mode = int(os.environ.get('MWD_TC_SPLIT_MODE', '0'))
+        if self._tc_posterior:
+            nb = int(self.lib.mwd_posterior_tc_scratch_bytes(self.K, self.D))
+            self.w_split = torch.empty((nb // 4,), dtype=torch.float32, device=dev)
         self._sum_scratch = torch.empty((256,), dtype=f64, device=dev)
         self._ll_out = torch.zeros((2,), dtype=f64, device=dev)   # [0]: loglik_sum, [1]: LL of the last EM iteration
 
@@ -202,8 +215,31 @@ class IKEngine(object):
                                                   _ptr(self.post), float(width), self.K,
                                                   _ptr(self.w_scratch), _ptr(self.pz), st))
         else:
-            _lib.check(lib.mwd_posterior_linear(_ptr(self.feats), self.feat_is_f64, R, self.D,
-                                                _ptr(self.post), self.K, _ptr(self.pz), st))
+            self._posterior_linear(_ptr(self.feats), R, _ptr(self.pz), st)
+
+    def _grad_partial(self, prob, accumulate, st):
+        """(conceptCounts - pz)^T [V,1] of one shard (chunk) into the partial tables: float64 DMMA kernel or the
+        tcgen05 split-TF32 kernel (MWD_MIXED_GRAD)."""
+        if self._tc_grad:
+            _lib.check(self.lib.mwd_ik_posterior_grad_tc_partial(C.byref(prob), _ptr(self.grad_partials), accumulate,
+                                                                 self._tc_split_mode, st))
+        else:
+            _lib.check(self.lib.mwd_ik_posterior_grad_partial(C.byref(prob), _ptr(self.grad_partials), accumulate, st))
+
+    def _grad_finish(self, st):
+        fn = self.lib.mwd_posterior_grad_tc_finish if self._tc_grad else self.lib.mwd_ik_posterior_grad_finish
+        _lib.check(fn(self.K, self.D, _ptr(self.grad_partials), _ptr(self.grad), st))
+
+    def _posterior_linear(self, f_ptr, R, pz_ptr, st):
+        """softmaxLayer of the linear class: float64 DMMA kernel, or (MWD_MIXED_POSTERIOR, fp32 features) the
+        tcgen05 split-TF32 kernel."""
+        lib = self.lib
+        if self._tc_posterior:
+            _lib.check(lib.mwd_posterior_linear_tc(f_ptr, R, self.D, _ptr(self.post), self.K, pz_ptr,
+                                                   _ptr(self.w_split), self._tc_split_mode, st))
+        else:
+            _lib.check(lib.mwd_posterior_linear(f_ptr, self.feat_is_f64, R, self.D, _ptr(self.post), self.K,
+                                                pz_ptr, st))
 
     def loglik_sum(self, width=1.0):
         """Sum over this shard of log(max(p(x|y), EPS)) under the current parameters (device scalar)."""
@@ -249,8 +285,7 @@ class IKEngine(object):
         if self.two_layer:
             timed('posterior_grad', self._two_layer_grads)
         else:
-            timed('posterior_grad', lambda: _lib.check(
-                lib.mwd_ik_posterior_grad(C.byref(prob), _ptr(self.grad_partials), _ptr(self.grad), st)))
+            timed('posterior_grad', lambda: (self._grad_partial(prob, 0, st), self._grad_finish(st)))
 
     def _two_layer_grads(self):
         """updateNeuralNetWeights :504-526: dW = (cC - pz)^T [h,1];  dV = ((cC - pz) W * (h>0))^T [v,1]."""
@@ -454,17 +489,15 @@ class IKEngine(object):
                 _lib.check(lib.mwd_posterior_gaussian(f_ptr, self.feat_is_f64, R, self.D, _ptr(self.post),
                                                       float(width), self.K, _ptr(self.w_scratch), pz_ptr, st))
             else:
-                _lib.check(lib.mwd_posterior_linear(f_ptr, self.feat_is_f64, R, self.D, _ptr(self.post),
-                                                    self.K, pz_ptr, st))
+                self._posterior_linear(f_ptr, R, pz_ptr, st)
             prob = self._chunk_problem(ch)
             _lib.check(lib.mwd_ik_estep(C.byref(prob), st))
             _lib.check(lib.mwd_ik_concept_counts(C.byref(prob), st))
             gprob = self._chunk_problem(ch, for_grad=True)
-            _lib.check(lib.mwd_ik_posterior_grad_partial(C.byref(gprob), _ptr(self.grad_partials),
-                                                         1 if c > 0 else 0, st))
+            self._grad_partial(gprob, 1 if c > 0 else 0, st)
         full = self._problem(with_cA=False)
         _lib.check(lib.mwd_ik_reduce_counts(C.byref(full), _ptr(self.counts), st))
-        _lib.check(lib.mwd_ik_posterior_grad_finish(self.K, self.D, _ptr(self.grad_partials), _ptr(self.grad), st))
+        self._grad_finish(st)
         self.allreduce()
         ll = self._keep_ll()
         self.mstep(lr, momentum, width)

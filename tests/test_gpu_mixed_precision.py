@@ -91,7 +91,8 @@ def test_twenty_em_iterations_mixed_vs_float64(gaussian):
         np.testing.assert_allclose(flatten_tables(lens, b[0]), flatten_tables(lens, a[0]), rtol=TOL, err_msg='init %d' % it)
         np.testing.assert_allclose(flatten_tables(lens, b[1]), flatten_tables(lens, a[1]), rtol=TOL, err_msg='trans %d' % it)
         np.testing.assert_allclose(b[2], a[2], rtol=TOL, atol=1e-300, err_msg='obs %d' % it)
-        np.testing.assert_allclose(b[3], a[3], rtol=TOL, atol=1e-9, err_msg='posterior parameter %d' % it)
+        # W / mus entries pass through zero: 1e-5 of the table's scale
+        np.testing.assert_allclose(b[3], a[3], rtol=TOL, atol=TOL * np.abs(a[3]).max(), err_msg='posterior parameter %d' % it)
         if (it + 1) % 10 == 0:
             lr /= 10
     # decode runs the float64 kernels in both modes: identical tables up to 1e-5 must give (near-)identical paths
