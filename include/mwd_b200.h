@@ -144,7 +144,7 @@ int mwd_posterior_linear_tc(const float* feats, int64_t n_regions, int feat_dim,
 
 /* updateSoftmaxWeight GEMM on the Blackwell tensor cores, the MWD_MIXED_GRAD path (csrc/posterior_grad_tc.cu):
  *   grad[k][d] = sum_r (concept_counts - pz)[r][k] * [feats,1][r][d]   -- image_phone_hmm_word_discoverer.py:475-488
- * split-TF32 operands, fp32 TMEM accumulation over at most 2048 rows, float64 per-CTA partial tables summed in fixed
+ * split-TF32 operands, fp32 TMEM accumulation over at most 512 rows, float64 per-CTA partial tables summed in fixed
  * order (deterministic).  partials [dev]: mwd_posterior_grad_tc_partials_len(K, D) doubles.  _partial with
  * accumulate == 0 zeroes the partial tables first; accumulate != 0 adds another chunk of the shard.  _finish writes
  * grad (K x (D+1)).  Uses p->feats (fp32), p->concept_counts, p->pz, p->n_regions, p->feat_dim, p->n_concepts.     */

@@ -25,11 +25,16 @@ class MwdError(RuntimeError):
 
 def mixed_bits(spec):
     """modelConfigs['posterior_precision'] / engine ``mixed_precision`` -> MWD_MIXED_* bits.
-    'float64' | None | 0: reference arithmetic everywhere (default); 'mixed': every floor-free part of the
-    iteration off the FP64 pipe; or an explicit int / '+'-joined subset of 'concept', 'posterior', 'grad'."""
+    'float64' | None | 0: reference arithmetic everywhere (default).
+    'mixed': the two floor-free GEMMs (softmaxLayer, updateSoftmaxWeight) on the tcgen05 tensor cores -- the set
+             that holds 1e-5 on log-likelihood and every table over 20 EM iterations (tests/test_gpu_mixed_precision.py).
+    'all':   additionally the updateConceptCounts chains in float32 (measured 1.4e-5 on obs after 20 iterations).
+    Or an explicit int / '+'-joined subset of 'concept', 'posterior', 'grad'."""
     if spec is None or spec is False or spec == 0 or spec == 'float64':
         return 0
     if spec is True or spec == 'mixed':
+        return MIXED_POSTERIOR | MIXED_GRAD
+    if spec == 'all':
         return MIXED_CONCEPT | MIXED_POSTERIOR | MIXED_GRAD
     if isinstance(spec, int):
         return spec & 7

@@ -6,7 +6,7 @@
 //
 // Opt-in (MWD_MIXED_GRAD): the gradient has no EPS floor (SURVEY 8a census).  Arithmetic: split-TF32 on both sides,
 //     v = v_hi + v_lo,  delta = d_hi + d_lo,   v*delta ~= v_hi d_hi + v_hi d_lo + v_lo d_hi     (error O(2^-22))
-// accumulated in fp32 TMEM for at most `flush_every` row-blocks, then added to a float64 partial table of the CTA
+// accumulated in fp32 TMEM for `flush_every` row-blocks (512 rows), then added to a float64 partial table of the CTA
 // (L2-resident); the CTAs' partials are summed in fixed order afterwards -> deterministic, no float atomics.
 //
 // The product is formed TRANSPOSED, grad^T[d][k], so that the big operand streams through TMA untouched:
@@ -336,7 +336,7 @@ extern "C" int mwd_ik_posterior_grad_tc_partial(const mwd_ik_problem* p, double*
   a.n_dblk = (D + 31) / 32;
   a.n_mtiles = (D + 127) / 128;
   a.split_mode = split_mode;
-  a.flush_every = 128;                 // 2048 rows per fp32 accumulation group
+  a.flush_every = 32;                  // 512 rows (64 truncating fp32 accumulates) per group, then float64
   a.cC = p->concept_counts;
   a.pz = p->pz;
   a.partials = partials;

@@ -110,10 +110,8 @@ class IKEngine(object):
         if self.two_layer:
             gp_len = max(gp_len, int(self.lib.mwd_outer_grad_partials_len(self.K, self.H)),
                          int(self.lib.mwd_outer_grad_partials_len(self.H, self.D)))
-        # tensor-core (tcgen05) gradient GEMM: opt-in (MWD_MIXED_GRAD), fp32 features, not the two-layer class
-        self._tc_grad = bool(self.mixed & _lib.MIXED_GRAD) and not self.two_layer \
-            and bool(self.lib.mwd_posterior_grad_tc_supported(self.feat_is_f64, self.D, self.K))
-        if self._tc_grad:
+        # the tensor-core (tcgen05) gradient GEMM keeps one partial table per SM: size for it up front when it can run
+        if not self.two_layer and self.lib.mwd_posterior_grad_tc_supported(self.feat_is_f64, self.D, self.K):
             gp_len = max(gp_len, int(self.lib.mwd_posterior_grad_tc_partials_len(self.K, self.D)))
         self.grad_partials = torch.empty((gp_len,), dtype=f64, device=dev)
         self._lens = np.ascontiguousarray(np.array(packed.lens, dtype=np.int32))
@@ -129,15 +127,23 @@ class IKEngine(object):
         need = int(self.lib.mwd_ik_scratch_bytes(C.byref(prob)))
         self.scratch = torch.empty((max(need, 8) // 8 + 1,), dtype=f64, device=dev)
         self.last_counts = None
-        # tensor-core (tcgen05) posterior of the linear class: opt-in, fp32 features only
-        self._tc_posterior = bool(self.mixed & _lib.MIXED_POSTERIOR) and not self.gaussian and not self.two_layer \
-            and bool(self.lib.mwd_posterior_tc_supported(self.feat_is_f64, self.D, self.K))
         self._tc_split_mode = int(os.environ.get('MWD_TC_SPLIT_MODE', '0'))
-        if self._tc_posterior:
-            nb = int(self.lib.mwd_posterior_tc_scratch_bytes(self.K, self.D))
-            self.w_split = torch.empty((nb // 4,), dtype=torch.float32, device=dev)
+        self.w_split = None
+        self.set_mixed(mixed_precision)
         self._sum_scratch = torch.empty((256,), dtype=f64, device=dev)
         self._ll_out = torch.zeros((2,), dtype=f64, device=dev)   # [0]: loglik_sum, [1]: LL of the last EM iteration
+
+    def set_mixed(self, spec):
+        """Select which floor-free parts leave the FP64 pipe (see _lib.mixed_bits); callable between iterations.
+        The tensor-core kernels need fp32 features and are not used by the two-layer class (posterior: linear class only)."""
+        self.mixed = _lib.mixed_bits(spec)
+        self._tc_posterior = bool(self.mixed & _lib.MIXED_POSTERIOR) and not self.gaussian and not self.two_layer \
+            and bool(self.lib.mwd_posterior_tc_supported(self.feat_is_f64, self.D, self.K))
+        self._tc_grad = bool(self.mixed & _lib.MIXED_GRAD) and not self.two_layer \
+            and bool(self.lib.mwd_posterior_grad_tc_supported(self.feat_is_f64, self.D, self.K))
+        if self._tc_posterior and self.w_split is None:
+            nb = int(self.lib.mwd_posterior_tc_scratch_bytes(self.K, self.D))
+            self.w_split = self.torch.empty((nb // 4,), dtype=self.torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):

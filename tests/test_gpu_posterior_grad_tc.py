@@ -1,6 +1,6 @@
 """The tcgen05 / TMA posterior-gradient kernel (mwd_ik_posterior_grad_tc_partial, csrc/posterior_grad_tc.cu) against
 the float64 DMMA kernel of the same library and NumPy:  grad = (cC - pz)^T [V, 1].
-Tolerance: 1e-5 of the gradient's scale (split-TF32 operands, fp32 accumulation over <= 2048 rows)."""
+Tolerance: 1e-5 of the gradient's scale (split-TF32 operands, fp32 accumulation over <= 512 rows)."""
 import ctypes as C
 
 import numpy as np
