@@ -516,14 +516,19 @@ extern "C" int mwd_ik_concept_counts(const mwd_ik_problem* p, void* stream) {
   MWD_CHECK_CUDA(cudaGetDevice(&dev));
   MWD_REQUIRE(dev >= 0 && dev < 16, "device ordinal %d outside [0,16)", dev);
   std::lock_guard<std::mutex> guard(g_const_mutex);
+  // under CUDA-graph capture (IKEngine.em_iteration_graph) the cross-stream event chain cannot be recorded: a captured
+  // iteration is single-stream by construction, and replays are ordered by the stream they are launched on
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  MWD_CHECK_CUDA(cudaStreamIsCapturing(st, &cap));
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
   if (!g_const_event[dev]) MWD_CHECK_CUDA(cudaEventCreateWithFlags(&g_const_event[dev], cudaEventDisableTiming));
-  else MWD_CHECK_CUDA(cudaStreamWaitEvent(st, g_const_event[dev], 0));   // previous user of the constant tables
+  else if (!capturing) MWD_CHECK_CUDA(cudaStreamWaitEvent(st, g_const_event[dev], 0));   // previous user of the constant tables
   // float32 chains need the scaled (P x K) float table: only for a real phone inventory, not for the dense
   // per-frame emission tables of the image-audio classes (P = number of frames)
   const bool f32 = (p->mixed_precision & MWD_MIXED_CONCEPT) && p->part_phone != nullptr &&
                    (int64_t)p->n_phone_types * p->n_concepts <= (1 << 22);
   int rc = f32 ? concept_counts_f32(p, st, dev) : concept_counts_f64(p, st);
   if (rc) return rc;
-  MWD_CHECK_CUDA(cudaEventRecord(g_const_event[dev], st));
+  if (!capturing) MWD_CHECK_CUDA(cudaEventRecord(g_const_event[dev], st));
   return 0;
 }

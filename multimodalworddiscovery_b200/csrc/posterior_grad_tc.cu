@@ -210,7 +210,13 @@ posterior_grad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const GradTcAr
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int k = c0 + j;
-              if (k < K) part[(size_t)k * (D + 1) + d] += (double)__uint_as_float(r[j]);
+              // fire-and-forget float64 add: element (k, d) of this CTA's table is only ever touched by THIS thread,
+              // in program order (same-address reductions of one thread stay ordered) -> deterministic, and the
+              // flush does not wait for a load round trip to L2 while the tensor core idles
+              if (k < K)
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(part + (size_t)k * (D + 1) + d),
+                             "d"((double)__uint_as_float(r[j]))
+                             : "memory");
             }
           }
         }

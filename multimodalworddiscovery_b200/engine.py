@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 from ._lib import IkMstepArgs, IkProblem, MwdError, NMAX, PartialSizes
 from .corpus import dense_to_tables, tables_to_dense
-from .dist import fixed_order_allreduce
+from .dist import fixed_order_allreduce, is_distributed
 
 
 def _ptr(t):
@@ -412,6 +412,45 @@ class IKEngine(object):
         ll = self._keep_ll()
         self.mstep(lr, momentum, width, freeze_trans)
         return ll
+
+    # ------------------------------------------------------------------ small corpora: one CUDA-graph replay per iteration
+    GRAPH_MAX_PAIRS = 50000
+
+    def em_iteration_auto(self, lr, momentum, width=1.0, freeze_trans=False):
+        """em_iteration, replayed from a CUDA graph when the shard is small enough to be launch-bound (the reference's
+        own use: 2 000 pairs x 20 epochs, ~35 kernel launches of a few microseconds each per iteration) and no
+        collective is on the path.  MWD_GRAPH=0 disables it."""
+        if self.pk.n_pairs > self.GRAPH_MAX_PAIRS or is_distributed(self.pg) or os.environ.get('MWD_GRAPH', '1') == '0':
+            return self.em_iteration(lr, momentum, width, freeze_trans=freeze_trans)
+        return self.em_iteration_graph(lr, momentum, width, freeze_trans)
+
+    def em_iteration_graph(self, lr, momentum, width=1.0, freeze_trans=False):
+        """One EM iteration as ONE graph launch.  Graphs are keyed by the by-value kernel parameters (lr, momentum,
+        width, flags); every buffer the kernels touch is owned by the engine, so replays see current parameters."""
+        torch = self.torch
+        key = (float(lr), float(momentum), float(width), bool(freeze_trans), self.mixed, self.toeplitz,
+               getattr(self, '_mstep_extra_flags', 0))
+        graphs = self.__dict__.setdefault('_graphs', {})
+        g = graphs.get(key)
+        if g is None:
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            keep = [t.clone() for t in self._param_tensors()]
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                # un-captured pass first: first-call allocations and module loads must not happen under capture
+                self.em_iteration(lr, momentum, width, with_cA=False, freeze_trans=freeze_trans)
+                self._copy_params(self._param_tensors(), keep)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self.em_iteration(lr, momentum, width, with_cA=False, freeze_trans=freeze_trans)
+            cur.wait_stream(side)
+            if len(graphs) >= 4:                       # lr decays by value: keep only the recent few
+                graphs.pop(next(iter(graphs)))
+            graphs[key] = g
+        g.replay()
+        self._ca_valid, self._cA_fresh, self._prev_width = True, False, width
+        return self._ll_out[1]
 
     # ------------------------------------------------------------------ streamed (host-resident) corpus
     def plan_chunks(self, n_chunks):

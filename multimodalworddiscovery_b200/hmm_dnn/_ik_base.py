@@ -301,7 +301,7 @@ class ImagePhoneHMMBase(object):
                     self.printAlignment(self.modelName + '_iter=' + str(epoch) + '_alignment', debug=False,
                                         _zero_concept_alignment=True)
                     maxLikelihood = likelihood
-            ll = eng.em_iteration(self.lr, self.momentum, width, freeze_trans=_freeze_trans)
+            ll = eng.em_iteration_auto(self.lr, self.momentum, width, freeze_trans=_freeze_trans)
             self._cA_valid = True
             if printStatus:
                 likelihood = float(ll) / N
@@ -516,7 +516,7 @@ class ImagePhoneHMMBase(object):
             eng.perturb_posterior(np.random.normal(size=shape), stepScale)   # :173
             # trainUsingEM(numIterations=inner, warmStart=True, printStatus=False) on the resident model (:174)
             for it in range(inner):
-                eng.em_iteration(self.lr, self.momentum, self._width())
+                eng.em_iteration_auto(self.lr, self.momentum, self._width())
                 if (it + 1) % 10 == 0:
                     self.lr /= 10
             self._cA_valid = True
