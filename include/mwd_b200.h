@@ -46,6 +46,7 @@ extern "C" {
 #define MWD_MIXED_CONCEPT 1
 #define MWD_MIXED_POSTERIOR 2
 #define MWD_MIXED_GRAD 4
+#define MWD_MIXED_RECURSION 8
 #define MWD_INIT_STRIDE MWD_NMAX
 #define MWD_TRANS_STRIDE (MWD_NMAX * MWD_NMAX)
 
@@ -116,7 +117,12 @@ typedef struct {
                                                        hi + lo, fp32 TMEM accumulators, float64 recombination
                                                        + softmax), features through TMA; linear class, fp32
                                                        features (mwd_posterior_linear_tc)
-                                  MWD_MIXED_GRAD       updateSoftmaxWeight GEMM likewise (mwd_ik_posterior_grad_tc) */
+                                  MWD_MIXED_GRAD       updateSoftmaxWeight GEMM likewise (mwd_ik_posterior_grad_tc)
+                                  MWD_MIXED_RECURSION  forward / backward lattice in scaled float32 (one power-of-two
+                                                       exponent per (pair, t)); every EPS floor is applied to the
+                                                       scaled value with the scaled threshold, the statistics handed
+                                                       to the count kernels and the phone counts stay float64
+                                                       (csrc/ik_estep_warp32.cu)                             */
   int32_t* concept_alignment;/* [dev] Ttot or NULL: argmax_k conceptCountsA[t][k] (first index on ties, the
                                 `concept_alignment` of printAlignment :628) written by mwd_ik_estep from
                                 the column sums it forms anyway -- 4 bytes per phone instead of the

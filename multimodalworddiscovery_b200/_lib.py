@@ -16,7 +16,7 @@ TRANS_STRIDE = NMAX * NMAX
 EPS = 1e-50
 
 
-MIXED_CONCEPT, MIXED_POSTERIOR, MIXED_GRAD = 1, 2, 4
+MIXED_CONCEPT, MIXED_POSTERIOR, MIXED_GRAD, MIXED_RECURSION = 1, 2, 4, 8
 
 
 class MwdError(RuntimeError):
@@ -35,12 +35,13 @@ def mixed_bits(spec):
     if spec is True or spec == 'mixed':
         return MIXED_POSTERIOR | MIXED_GRAD
     if spec == 'all':
-        return MIXED_CONCEPT | MIXED_POSTERIOR | MIXED_GRAD
+        return MIXED_CONCEPT | MIXED_POSTERIOR | MIXED_GRAD | MIXED_RECURSION
     if isinstance(spec, int):
-        return spec & 7
+        return spec & 15
     bits = 0
     for part in str(spec).split('+'):
-        bits |= {'concept': MIXED_CONCEPT, 'posterior': MIXED_POSTERIOR, 'grad': MIXED_GRAD}[part.strip()]
+        bits |= {'concept': MIXED_CONCEPT, 'posterior': MIXED_POSTERIOR, 'grad': MIXED_GRAD,
+                 'recursion': MIXED_RECURSION}[part.strip()]
     return bits
 
 

@@ -697,6 +697,8 @@ extern "C" int64_t mwd_ik_scratch_bytes(const mwd_ik_problem* p) {
     if (bytes > need) need = bytes;
     bytes = estep_warp_scratch(p->bucket_n[b], p->n_concepts, p->n_phone_types, p->bucket_tmax[b], np_) * (int64_t)sizeof(double);
     if (bytes > need) need = bytes;
+    bytes = estep_warp32_scratch(p->bucket_n[b], p->n_concepts, p->n_phone_types, p->bucket_tmax[b], np_) * (int64_t)sizeof(double);
+    if (bytes > need) need = bytes;
   }
   return need;
 }
@@ -711,7 +713,12 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     const int64_t lo = p->bucket_lo[b], hi = p->bucket_lo[b + 1];
     if (hi <= lo) continue;
     MWD_REQUIRE(n >= 1 && n <= MWD_NMAX, "bucket %d: n=%d outside [1,%d]", b, n, MWD_NMAX);
-    const int64_t warp_scr = estep_warp_scratch(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo);
+    // scaled-float32 lattice (MWD_MIXED_RECURSION) where an instantiation exists and the caller consumes phone counts
+    const int64_t warp32_scr = ((p->mixed_precision & MWD_MIXED_RECURSION) && p->part_phone != nullptr)
+                                   ? estep_warp32_scratch(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo) : 0;
+    const bool use_warp32 = warp32_scr > 0;
+    const int64_t warp_scr = use_warp32 ? warp32_scr
+                                        : estep_warp_scratch(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo);
     const bool use_warp = warp_scr > 0;
     EstepPlan pl = plan_bucket(n, p->n_concepts, p->n_phone_types, p->bucket_tmax[b], hi - lo);
     if (use_warp) {   // the warp-per-pair kernel plans its own launch; only the scratch check applies
@@ -756,7 +763,8 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
     a.ll_only = ll_only;
     a.eps = p->no_floor ? 0.0 : MWD_EPS;
     int rc = 0;
-    if (use_warp) rc = estep_warp_launch(a, st);
+    if (use_warp32) rc = estep_warp32_launch(a, st);
+    else if (use_warp) rc = estep_warp_launch(a, st);
     else switch (pl.KG) {
 #define MWD_KG(G) case G: rc = launch_estep_kg<G>(a, pl, st); break;
       MWD_KG(1) MWD_KG(2) MWD_KG(3) MWD_KG(4) MWD_KG(5) MWD_KG(6) MWD_KG(7) MWD_KG(8)

@@ -51,5 +51,9 @@ __device__ __forceinline__ bool argmax_better(double v, double best) {
 bool estep_warp_supported(int n, int K, int P);
 int64_t estep_warp_scratch(int n, int K, int P, int Tmax, int64_t npairs);
 int estep_warp_launch(EstepArgs a, cudaStream_t st);
+// Scaled-float32 form of the warp-per-pair kernel (ik_estep_warp32.cu, MWD_MIXED_RECURSION); scratch == 0: no
+// instantiation / shared memory for this shape, the float64 kernels run instead.
+int64_t estep_warp32_scratch(int n, int K, int P, int Tmax, int64_t npairs);
+int estep_warp32_launch(EstepArgs a, cudaStream_t st);
 
 }  // namespace mwd

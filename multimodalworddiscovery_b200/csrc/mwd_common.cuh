@@ -36,7 +36,7 @@ constexpr int kNMax = MWD_NMAX;
 constexpr int kPairsPerCta = 4;   // pairs processed in lock-step by one estep CTA
 constexpr int kLanesPerRow = 8;   // threads that share one (pair, region) row of the (i,k) lattice
 constexpr int kGradSplits = 74;   // row splits of the posterior-gradient GEMM (x4 d-tiles = 2 CTAs/SM)
-constexpr int kEstepCtasPerSm = 12; // rows of the per-CTA (per-warp for K1w) partial tables per SM
+constexpr int kEstepCtasPerSm = 16; // rows of the per-CTA (per-warp for K1w: 12, K1w32: 16) partial tables per SM
 
 int sm_count();
 int estep_grid_rows();

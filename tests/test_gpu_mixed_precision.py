@@ -66,7 +66,62 @@ def test_concept_chains_float32_full_shapes(K, n_choices):
     np.testing.assert_allclose(out[1], out[0], rtol=TOL, atol=1e-12)
 
 
-@pytest.mark.parametrize('gaussian,mode,tol', [(False, 'mixed', 1e-5), (True, 'mixed', 1e-5), (False, 'all', 3e-5)])
+def _estep_outputs(eng, width):
+    eng.estep(width)
+    n = eng.pk.n_pairs
+    return (eng.pair_ll[:n].cpu().numpy().copy(), eng.counts.cpu().numpy().copy(),
+            eng.concept_alignment().cpu().numpy().copy())
+
+
+def _check_recursion(out32, out64, K, P, tol=TOL):
+    ll32, c32, ca32 = out32
+    ll64, c64, ca64 = out64
+    np.testing.assert_allclose(ll32, ll64, rtol=1e-6, atol=1e-6)          # per-pair log-likelihood (|ll| ~ 20 .. 115)
+    pe = P * K
+    for name, sl in (('phone', slice(0, pe)), ('init+trans', slice(pe, len(c64) - 1))):
+        scale = np.abs(c64[sl]).max()
+        assert np.abs(c32[sl] - c64[sl]).max() <= tol * scale, (name, np.abs(c32[sl] - c64[sl]).max() / scale)
+    np.testing.assert_allclose(c32[-1], c64[-1], rtol=1e-7)               # summed log-likelihood
+    assert (ca32 == ca64).mean() > 0.995                                  # argmax flips only on float32-level ties
+
+
+@pytest.mark.parametrize('case', ['mixed_linear', 'long_floor_linear', 'short_toeplitz_linear', 'mixed_gaussian', 'tiny_linear'])
+def test_recursion_float32_vs_float64_on_goldens(case):
+    """Scaled-float32 lattice (MWD_MIXED_RECURSION) vs the float64 kernels on the reference-pinned cases, including
+    the EPS-floor regime (long_floor: every pair floored) and the mixed one."""
+    g = load_ik(case)
+    p = oracle_params_from_golden(g)
+    gaussian = g['kind'] == 'gaussian'
+    out = []
+    for mixed in (0, 'recursion'):
+        eng = _engine(g['feats_list'], g['phones_list'], g['K'], g['P'], gaussian, mixed, np.float64)
+        eng.set_params(p['init'], p['trans'], p['obs'], p['mus'] if gaussian else p['W'])
+        out.append(_estep_outputs(eng, g['width']))
+    _check_recursion(out[1], out[0], g['K'], g['P'])
+
+
+@pytest.mark.parametrize('K,n_choices,T_hi', [(65, [5], 125), (65, list(range(1, 11)), 125), (100, [1, 2, 3, 4, 5, 6, 7, 8], 125),
+                                             (40, [3, 9, 12], 60), (80, [2, 5, 10], 90), (50, [1, 4, 7], 125)])
+def test_recursion_float32_full_shapes(K, n_choices, T_hi):
+    rng = np.random.default_rng(K + len(n_choices))
+    P, D = 49, 64
+    feats, phones, _ = _synth(rng, 150, K, P, D, n_choices, 15, T_hi, scale=1.0)
+    W = 0.1 * rng.standard_normal((K, D + 1))
+    lens = sorted({v.shape[0] for v in feats})
+    init = {m: (lambda v: v / v.sum())(rng.random(m) + 0.5) for m in lens}
+    trans = {m: (lambda v: v / v.sum(1, keepdims=True))(rng.random((m, m)) + 0.5) for m in lens}
+    obs = rng.random((K, P)) ** 6 + 1e-9                       # peaky rows: six orders of magnitude inside a row
+    obs /= obs.sum(1, keepdims=True)
+    out = []
+    for mixed in (0, 'recursion'):
+        eng = _engine(feats, phones, K, P, False, mixed)
+        eng.set_params(init, trans, obs, W)
+        out.append(_estep_outputs(eng, 1.0))
+    _check_recursion(out[1], out[0], K, P)
+
+
+@pytest.mark.parametrize('gaussian,mode,tol', [(False, 'mixed', 1e-5), (True, 'mixed', 1e-5), (False, 'all', 3e-5),
+                                               (False, 'posterior+grad+recursion', 1e-5), (True, 'grad+recursion', 1e-5)])
 def test_twenty_em_iterations_mixed_vs_float64(gaussian, mode, tol):
     """Acceptance gate of the mixed path: 20 iterations from the same start, LL and every table to 1e-5
     ('mixed' = tensor-core GEMMs; 'all' adds the float32 concept chains, which reach 1.4e-5 on obs).
