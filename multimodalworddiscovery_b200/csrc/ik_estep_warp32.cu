@@ -51,16 +51,13 @@ __device__ __forceinline__ float row_sum_head32(float v, int j) {
   }
 }
 
-// 2^e as a double / float (e within the normal range)
-__device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+// 2^e as a double / float.  pow2d clamps below at 2^-1022: raw values under that are 0 or denormal in the reference too
+__device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(max(e, -1022) + 1023) << 52); }
 __device__ __forceinline__ float pow2f(int e) { return __int_as_float((e + 127) << 23); }
 // binary exponent of a positive normal float
 __device__ __forceinline__ int expof(float m) { return ((__float_as_int(m) >> 23) & 0xff) - 127; }
-// un-scale: x * 2^e in float64, e clamped into the double range (raw values below 2^-1022 are 0 in the reference too)
-__device__ __forceinline__ double unscale(float x, int e) {
-  if (e < -1000) return (double)x * pow2d(-1000) * pow2d(e + 1000 < -1000 ? -1000 : e + 1000);
-  return (double)x * pow2d(e);
-}
+// un-scale: x * 2^e in float64
+__device__ __forceinline__ double unscale(float x, int e) { return (double)x * pow2d(e); }
 // argmax over a warp of non-negative floats, first index on ties (np.argmax); lanes without a candidate pass (0, INT_MAX)
 __device__ __forceinline__ int warp_argmax_nonneg32(float v, int k) {
   const unsigned b = __float_as_uint(v);
@@ -107,6 +104,10 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
     for (int k = lane; k < K; k += 32) obsS[x * K + k] = (float)(a.obsT[(size_t)x * K + k] * sc);
   }
   __syncthreads();
+
+  // EPS = epsm * 2^epse (epsm in [0.5, 1)); 0 for the un-floored classes
+  int epse = 0;
+  const float epsm = (float)frexp(eps, &epse);
 
   const float d_i = (float)a.trans[i * N + i];
   const float pi_i = (float)a.init[i];
@@ -251,10 +252,12 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
         }
       }
       const int eg = eat + eb;                    // exponent of gamma^, dg^
-      // the EPS floor in scaled units; beyond float32 every entry of the step is floored
-      const double epsS = eps * ((-eg > 1000) ? pow2d(1000) : ((-eg < -1000) ? 0.0 : pow2d(-eg)));
-      const bool all_floored = epsS > 1e30;
-      const float epsf = all_floored ? 0.0f : (float)epsS;
+      // the EPS floor in scaled units, EPS * 2^-eg = epsm * 2^E: beyond 2^100 every entry of the step is floored
+      // (gamma^ <= ~8), below 2^-125 it cannot matter; no float64 arithmetic on this path
+      const int E = epse - eg;
+      const bool all_floored = (epsm > 0.0f) && (E > 100);
+      const float epsf = (all_floored || E < -125) ? 0.0f : epsm * pow2f(E);
+      const double sg = pow2d(eg);
       double tabv[KC];
       double* trow = tab + x * K + lane;
 #pragma unroll
@@ -299,8 +302,8 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       rr = row_sum_head32<LPR>(rr, j);
       if (head) {         // row statistics of this step for the count post-pass, un-scaled float64
         // every entry floored: the K concepts of the row contribute EPS each
-        __stcs(st + (t * 4 + 1) * N, all_floored ? (double)K * eps : unscale(sumF, eg));
-        __stcs(st + (t * 4 + 2) * N, unscale(dg, eg));
+        __stcs(st + (t * 4 + 1) * N, all_floored ? (double)K * eps : (double)sumF * sg);
+        __stcs(st + (t * 4 + 2) * N, (double)dg * sg);
         __stcs(st + (t * 4 + 3) * N, unscale(rr, ebo));
       }
       float wn = 0.0f;
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       w = wn;
       eb = ebo;
       // conceptCountsA[t][k] = sum_i gamma_t[i][k] / max(L, EPS);  phoneCounts[k][x_t] += ...  (:430,:233,:235)
-      const double gsc = ((eg < -1000) ? pow2d(-1000) * pow2d(eg + 1000 < -1000 ? -1000 : eg + 1000) : pow2d(eg)) * inorm;
+      const double gsc = sg * inorm;
 #pragma unroll
       for (int m = 0; m < KC; ++m) {
         const double v = (double)cs[m] * gsc;
@@ -327,6 +330,13 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       }
     };
 
+    auto drop_slice = [&](int c) {
+      // checkpoint slice c is dead: drop it from L2 instead of letting it be written back to HBM
+      for (int ln = lane; ln < SL / 32; ln += 32) {
+        const float* dead = scr + (size_t)c * SL + ln * 32;
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead) : "memory");
+      }
+    };
     const int nblk = (T + 1) / 2;
     int par = 0;
     for (int c = nblk - 1; c >= 0; --c) {
@@ -356,6 +366,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
         bwd_step(t0, x0, shS[x0], e0, a0, o0, buf + par * (N * KS));
         par ^= 1;
       }
+      drop_slice(c);
     }
   }
 }
