@@ -635,8 +635,8 @@ def gpu_arm(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None,
-            'dtype': 'f64' if not eng.mixed else 'f64 (recursion, counts, concept chains, softmax, M-step) + split-tf32 '
-                     'tensor-core GEMMs with fp32 TMEM accumulation (precision %s)' % args.mixed,
+            'dtype': 'f64' if not eng.mixed else 'f64 (concept chains, counts, statistics, softmax, M-step) + scaled f32 forward/'
+                     'backward lattice + split-tf32 tensor-core GEMMs with fp32 TMEM accumulation (precision %s)' % args.mixed,
             'data': 'synthetic',
             'config': workload_config(args, args.pairs),
             'avg_log_likelihood': avg_ll,
@@ -652,7 +652,7 @@ def gpu_arm(args):
                          'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650',
                          'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pk.n_pairs,
-                         'note': 'path is FP64-pipe bound (SURVEY 8d), see DESIGN.md'},
+                         'note': 'the path is bound by the FP32 / FP64 issue rate, not HBM (SURVEY 8d), see DESIGN.md'},
             'fp64_roofline': {'bound': 'fp64 pipe (DFMA/DMMA)', 'achieved': args.pairs * fpp / (ms_step * 1e-3) / 1e12 / world,
                               'peak': fp64_peak, 'unit': 'TFLOP/s per GPU', 'frac': args.pairs * fpp / (ms_step * 1e-3) / 1e12 / world / fp64_peak,
                               'algorithmic_flop_per_pair': fpp,
@@ -874,7 +874,7 @@ def main():
     ap.add_argument('--model', default=None, choices=['linear', 'gaussian'],
                     help='image posterior: linear softmax or RBF (default: the config\'s)')
     ap.add_argument('--mixed', default='mixed',
-                    help="precision of the floor-free GEMMs: 'mixed' (default: tcgen05 split-TF32 tensor-core kernels, "
+                    help="'mixed' (default: tcgen05 split-TF32 tensor-core GEMMs + scaled-float32 forward/backward lattice, "
                          "validated at 1e-5 against float64 in the same run) | 'float64' (reference arithmetic everywhere) "
                          "| 'all' (+ float32 concept chains) | subset like 'posterior+grad'")
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')

@@ -386,12 +386,16 @@ struct WarpPlan {
 };
 
 // (n, KG) instantiations: K = 65 (MSCOCO, run_image2phone.py:43) and K = 50 / 100 (Flickr30k,
-// run_image2phone.py:73 / image_phone_hmm_word_discoverer.py:735) for the n they are fast for.
+// run_image2phone.py:73 / image_phone_hmm_word_discoverer.py:735) for the n they are fast for, plus K = 40 / 80.
+// Other concept counts run the generic CTA-per-4-pairs kernel (ik_estep.cu).
 #define MWD_WARP_COMBOS(X)                                                              \
   X(1, 2) X(1, 3) X(1, 4) X(2, 4) X(2, 5) X(2, 7) X(3, 5) X(3, 7) X(3, 10) X(4, 7) X(4, 9) \
   X(4, 13) X(5, 9) X(5, 11) X(6, 10) X(6, 13)                                             \
   X(5, 17) X(7, 13) X(7, 17) X(8, 13) X(8, 17) X(9, 17) X(9, 22) X(10, 17) X(10, 22)                 \
-  X(6, 20) X(7, 25) X(8, 25)
+  X(6, 20) X(7, 25) X(8, 25)                                                                          \
+  /* K = 40 and K = 80 (any n <= 8, K = 40 also n = 9, 10): no drop to the CTA-per-4-pairs kernel */ \
+  X(2, 3) X(3, 4) X(4, 5) X(5, 7) X(6, 8) X(7, 10) X(8, 10) X(9, 14) X(10, 14)                       \
+  X(3, 8) X(4, 10) X(5, 14) X(6, 16) X(7, 20) X(8, 20)
 // register-block variant: compiled (and the default) for the MSCOCO concept count K = 65, n <= 8 (at
 // n = 5 it measured 55.1 vs 60.3 ms at 1M pairs); MWD_ESTEPW_RB=0 selects the shared-memory block
 // variant instead

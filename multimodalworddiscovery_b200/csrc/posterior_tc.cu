@@ -89,6 +89,18 @@ struct PostTcArgs {
 __host__ __device__ inline int pt_stage_bytes(int NPAD) { return 2 * PT_A_BYTES + 2 * NPAD * PT_BK * 4; }
 __host__ __device__ inline int pt_stage_row_doubles(int K) { return K | 1; }   // odd stride: conflict-free rows
 
+// exp(x) for x <= 0 on the SFU: 2^(x log2 e) with the integer part moved into the float64 exponent and the fraction
+// (|f| <= 1/2, float32-exact to 3e-8) through ex2.approx (relative error 2^-22).  The row softmax needs 65 of these per
+// region; libm's float64 exp (~28 FP64-pipe instructions each) made the epilogue, not the tensor core, the critical path.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double t = fmax(x, -708.0) * 1.4426950408889634;
+  const double r = rint(t);
+  float p;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"((float)(t - r)));
+  const double v = __longlong_as_double(__double_as_longlong((double)p) + ((long long)(int)r << 52));
+  return x < -708.0 ? 0.0 : v;
+}
+
 __global__ void __launch_bounds__(PT_THREADS, 1)
 posterior_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const PostTcArgs a) {
@@ -247,16 +259,22 @@ posterior_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       double m = -1.0 / 0.0;
       for (int c0 = 0; c0 < NPAD; c0 += 16) {
         double x[16];
+        float xc[16];                       // the small sums (2^-11 of the large ones) add up in float32
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = 0.0;
+        for (int j = 0; j < 16; ++j) { x[j] = 0.0; xc[j] = 0.0f; }
         for (int ch = 0; ch < a.chunks; ++ch) {
           uint32_t rm[16], rc[16];
           tmem_ld16(taddr + ch * 2 * NPAD + c0, rm);
           tmem_ld16(taddr + ch * 2 * NPAD + NPAD + c0, rc);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] += (double)__uint_as_float(rm[j]) + (double)__uint_as_float(rc[j]);
+          for (int j = 0; j < 16; ++j) {
+            x[j] += (double)__uint_as_float(rm[j]);
+            xc[j] += __uint_as_float(rc[j]);
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] += (double)xc[j];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = c0 + j;
@@ -271,7 +289,7 @@ posterior_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_arrive(tmem_empty);              // the accumulators may be overwritten by the next tile
       double ssum = 0.0;
       for (int k = 0; k < K; ++k) {
-        const double e = exp(my[k] - m);
+        const double e = exp_nonpos(my[k] - m);
         my[k] = e;
         ssum += e;
       }

@@ -69,6 +69,13 @@ class IKAudioEngine(IKEngine):
             p.obsT = _ptr(self.E)
         return p
 
+    def _param_tensors(self):
+        # the audio posterior weights are model parameters too (snapshot / restore, CUDA-graph warm-up)
+        ts = IKEngine._param_tensors(self)
+        if self._audio_ready:
+            ts.append(self.WA)
+        return ts
+
     def set_audio_param(self, WA):
         WA = np.ascontiguousarray(np.asarray(WA, dtype=np.float64))
         if WA.shape != tuple(self.WA.shape):

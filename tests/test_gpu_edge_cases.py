@@ -79,6 +79,10 @@ def test_static_n_kernels_all_lengths():
     _run(f, x, 65, 11)
     f, x = _corpus(rng, 24, [3, 7, 10], 2, 20, K=100, P=9, D=6)           # KG = 13
     _run(f, x, 100, 9, kind='gaussian')
+    f, x = _corpus(rng, 40, list(range(1, 11)), 2, 25, K=40, P=11, D=6)   # K = 40: warp kernel for every n <= 10
+    _run(f, x, 40, 11)
+    f, x = _corpus(rng, 36, list(range(1, 11)), 2, 25, K=80, P=9, D=6)    # K = 80: warp kernel for n <= 8, generic for 9, 10
+    _run(f, x, 80, 9)
 
 
 def test_large_phone_inventory_and_long_captions():
