@@ -20,6 +20,8 @@
 //   D = up to 4 accumulators (D <= 512) x NPAD columns of TMEM
 // Warp roles: 0 TMA producer | 1 UMMA issuer | 2-5 feature splitter (v -> v_hi, v_lo) | 6-9 TMEM flush |
 //             10-13 delta builder.  One persistent CTA per SM owns a contiguous range of row-blocks.
+#include <stdlib.h>
+
 #include "mwd_common.cuh"
 #include "tc_common.cuh"
 
@@ -44,6 +46,7 @@ struct GradTcArgs {
   int32_t stages;
   int32_t split_mode;
   int32_t flush_every;   // row-blocks per fp32 accumulation group
+  int32_t prefetch;      // row-blocks of features prefetched into L2 ahead of the TMA loads
   const double* cC;
   const double* pz;
   double* partials;      // [gridDim.x][K][D+1], pre-zeroed or carrying earlier chunks; always accumulated into
@@ -57,7 +60,8 @@ __host__ __device__ inline int gt_stage_bytes(int n_dblk, int NPAD) {
 
 template <int NKK>   // ceil(NPAD / 32): concept columns handled per delta-builder lane
 __global__ void __launch_bounds__(GT_THREADS, 1)
-posterior_grad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const GradTcArgs a) {
+posterior_grad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmPF,
+                         const GradTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -103,9 +107,20 @@ posterior_grad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const GradTcAr
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
+      // L2 prefetch a.prefetch row-blocks ahead (16 rows x 256 dims per instruction, un-swizzled map)
+      int64_t pf = 0;
+      auto prefetch_next = [&]() {
+        if (pf < my_rb) {
+          const int row = (int)((rb_lo + pf) * GT_BR);
+          for (int c = 0; c < D; c += 256) tma_prefetch_l2_2d(&tmPF, c, row);
+          ++pf;
+        }
+      };
+      for (int i = 0; i < a.prefetch; ++i) prefetch_next();
       for (int64_t i = 0; i < my_rb; ++i) {
         const int s = (int)(i % S);
         const uint32_t ph = (uint32_t)(i / S) & 1u;
+        prefetch_next();
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* st = stage_base + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_raw[s], (uint32_t)a_bytes);
@@ -343,6 +358,8 @@ extern "C" int mwd_ik_posterior_grad_tc_partial(const mwd_ik_problem* p, double*
   a.n_mtiles = (D + 127) / 128;
   a.split_mode = split_mode;
   a.flush_every = 32;                  // 512 rows (64 truncating fp32 accumulates) per group, then float64
+  a.prefetch = 0;          // measured: no gain at any distance, kept as a knob (MWD_TC_PREFETCH)
+  if (const char* e = getenv("MWD_TC_PREFETCH")) a.prefetch = atoi(e) < 0 ? 0 : atoi(e);
   a.cC = p->concept_counts;
   a.pz = p->pz;
   a.partials = partials;
@@ -355,6 +372,10 @@ extern "C" int mwd_ik_posterior_grad_tc_partial(const mwd_ik_problem* p, double*
   CUtensorMap tmA;
   if (int rc = tc::make_tmap_f32_2d(&tmA, p->feats, (uint64_t)p->n_regions, (uint64_t)D, (uint64_t)D * 4, GT_BR, /*atom32=*/true))
     return rc;
+  CUtensorMap tmPF;
+  if (int rc = tc::make_tmap_f32_2d_plain(&tmPF, p->feats, (uint64_t)p->n_regions, (uint64_t)D, (uint64_t)D * 4, GT_BR,
+                                          (uint32_t)(D < 256 ? D : 256)))
+    return rc;
   const int64_t grid = (a.n_rb + a.rb_per_cta - 1) / a.rb_per_cta;
   const int nkk = (a.NPAD + 31) / 32;
 #define MWD_GT_LAUNCH(N)                                                                                        \
@@ -365,7 +386,7 @@ extern "C" int mwd_ik_posterior_grad_tc_partial(const mwd_ik_problem* p, double*
                                           GT_SMEM_BUDGET));                                                     \
       attr_set = true;                                                                                          \
     }                                                                                                           \
-    posterior_grad_tc_kernel<N><<<(unsigned)grid, GT_THREADS, smem, st>>>(tmA, a);                              \
+    posterior_grad_tc_kernel<N><<<(unsigned)grid, GT_THREADS, smem, st>>>(tmA, tmPF, a);                             \
   } break;
   switch (nkk) {
     MWD_GT_LAUNCH(1) MWD_GT_LAUNCH(2) MWD_GT_LAUNCH(3) MWD_GT_LAUNCH(4)

@@ -23,6 +23,8 @@
 //               (rounds toward zero) every fp32 accumulate -- measured: mean logit error = 0.5 ulp x #accumulates --
 //               so the error shrinks ~1/C.  The accumulators are released as soon as the epilogue has copied them
 //               to shared memory (first pass), which is what keeps a single buffer cheap.
+#include <stdlib.h>
+
 #include "mwd_common.cuh"
 #include "tc_common.cuh"
 
@@ -58,6 +60,21 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return 0;
 }
 
+int make_tmap_f32_2d_plain(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                           uint32_t box_rows, uint32_t box_cols) {
+  encode_tiled_fn enc = get_encode_tiled();
+  MWD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MWD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (prefetch map) failed (%d)", (int)r);
+  return 0;
+}
+
 }  // namespace tc
 
 namespace {
@@ -81,6 +98,7 @@ struct PostTcArgs {
   int32_t split_mode;    // 0: v_hi = rn_tf32(v) written in place; 1: v_hi = the raw word (hardware truncation)
   int32_t chunks;        // accumulator chunks over the feature dimension
   int32_t bulk_ok;       // pz is 16-byte aligned: whole-warp bulk stores allowed
+  int32_t prefetch;      // k-blocks of features prefetched into L2 ahead of the TMA loads
   int32_t ldw;           // D + 1 (row stride of W, bias in the last column)
   const double* W;
   double* pz;
@@ -151,10 +169,22 @@ posterior_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
       uint32_t it = 0;
+      // L2 prefetch runs a.prefetch k-blocks ahead of the loads: the shared-memory ring (3 stages) alone keeps too few
+      // bytes in flight to cover HBM latency (measured 41 % of the HBM peak without it)
+      int64_t pf_tile = blockIdx.x;
+      int pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile < a.n_tiles) {
+          tma_prefetch_l2_2d(&tmA, pf_kb * PT_BK, (int)(pf_tile * PT_BM));
+          if (++pf_kb == a.n_kblocks) { pf_kb = 0; pf_tile += gridDim.x; }
+        }
+      };
+      for (int i = 0; i < a.prefetch; ++i) prefetch_next();
       for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
+          prefetch_next();
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* st = stage_base + (size_t)s * stage_bytes;
           mbar_arrive_expect_tx(&full_raw[s], PT_A_BYTES + 2 * w_bytes);
@@ -388,6 +418,8 @@ extern "C" int mwd_posterior_linear_tc(const float* feats, int64_t n_regions, in
   a.chunks = 512 / (2 * NPAD) > 4 ? 4 : 512 / (2 * NPAD);
   if (a.chunks > a.n_kblocks) a.chunks = a.n_kblocks;
   a.bulk_ok = (((uintptr_t)pz & 15) == 0) ? 1 : 0;
+  a.prefetch = 0;          // measured: no gain at any distance (the kernel is not HBM-latency bound), kept as a knob
+  if (const char* e = getenv("MWD_TC_PREFETCH")) a.prefetch = atoi(e) < 0 ? 0 : atoi(e);
   a.ldw = D + 1;
   a.W = W;
   a.pz = pz;

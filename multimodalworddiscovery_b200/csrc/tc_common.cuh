@@ -81,6 +81,11 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "l"(policy)
       : "memory");
 }
+// fetch a box into L2 only (no shared memory, no barrier): decouples HBM latency from the depth of the smem ring
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -177,6 +182,9 @@ encode_tiled_fn get_encode_tiled();
 // tcgen05 accepts for MN-major 32-bit operands -- tools/umma_layout_probe.py)
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                      uint32_t box_rows, bool atom32 = false);
+// un-swizzled map with a [box_rows][box_cols] box, only used for L2 prefetches (box_cols <= 256)
+int make_tmap_f32_2d_plain(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                           uint32_t box_rows, uint32_t box_cols);
 
 }  // namespace tc
 }  // namespace mwd
