@@ -127,6 +127,14 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
   double* tab = a.part_phone + (size_t)gw * P * K;
   const float* obs_j = obsS + j;
 
+  int ccol[KC];
+  bool cok[KC];
+#pragma unroll
+  for (int m = 0; m < KC; ++m) {
+    cok[m] = lane + 32 * m < K;
+    ccol[m] = min(lane + 32 * m, KS0 - 1);
+  }
+
   auto load_obs = [&](float (&o)[KG], int x) {
     const float* orow = obs_j + x * K;
 #pragma unroll
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       double tabv[KC];
       double* trow = tab + x * K + lane;
 #pragma unroll
-      for (int m = 0; m < KC; ++m) tabv[m] = (tab_on && lane + 32 * m < K) ? __ldcg(trow + 32 * m) : 0.0;
+      for (int m = 0; m < KC; ++m) tabv[m] = (tab_on && cok[m]) ? __ldcg(trow + 32 * m) : 0.0;
       float* grow = gslice + i * KS + j;
       float sumF = 0.0f, dg = 0.0f, rr = 0.0f, sumF_b = 0.0f, dg_b = 0.0f, rr_b = 0.0f;
 #pragma unroll
@@ -287,24 +295,31 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       dg = (dg + dg_b) * d_i;
       const int ebo = eb - sh;                    // exponent of the new bo / rr / w
       __syncwarp();
-      const float* col = gslice + lane;
+      // column sums: unconditional loads from a clamped column (lanes past K re-read column KS0-1: a broadcast, no
+      // bank conflict), masked afterwards -- the guarded form compiles to one branch region per column chunk
       float cs[KC];
 #pragma unroll
       for (int m = 0; m < KC; ++m) {
-        cs[m] = 0.0f;
-        if (lane + 32 * m < K) {
+        const float* col = gslice + ccol[m];
+        float acc = 0.0f;
 #pragma unroll
-          for (int ii = 0; ii < N; ++ii) cs[m] += col[ii * KS + 32 * m];
-        }
+        for (int ii = 0; ii < N; ++ii) acc += col[ii * KS];
+        cs[m] = cok[m] ? acc : 0.0f;
       }
       sumF = row_sum_head32<LPR>(sumF, j);
       dg = row_sum_head32<LPR>(dg, j);
       rr = row_sum_head32<LPR>(rr, j);
-      if (head) {         // row statistics of this step for the count post-pass, un-scaled float64
+      {                   // row statistics of this step for the count post-pass, un-scaled float64 (head lanes store)
         // every entry floored: the K concepts of the row contribute EPS each
-        __stcs(st + (t * 4 + 1) * N, all_floored ? (double)K * eps : (double)sumF * sg);
-        __stcs(st + (t * 4 + 2) * N, (double)dg * sg);
-        __stcs(st + (t * 4 + 3) * N, unscale(rr, ebo));
+        const double v1 = all_floored ? (double)K * eps : (double)sumF * sg;
+        const double v2 = (double)dg * sg;
+        const double v3 = unscale(rr, ebo);
+        double* sp = st + (t * 4 + 1) * N;
+        if (head) {
+          __stcs(sp, v1);
+          __stcs(sp + N, v2);
+          __stcs(sp + 2 * N, v3);
+        }
       }
       float wn = 0.0f;
 #pragma unroll
@@ -316,15 +331,15 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
 #pragma unroll
       for (int m = 0; m < KC; ++m) {
         const double v = (double)cs[m] * gsc;
-        if (tab_on && lane + 32 * m < K) __stcg(trow + 32 * m, tabv[m] + v);
-        if (a.cA_out && lane + 32 * m < K) a.cA_out[(p0 + t) * K + lane + 32 * m] = v;
+        if (tab_on && cok[m]) __stcg(trow + 32 * m, tabv[m] + v);
+        if (a.cA_out && cok[m]) a.cA_out[(p0 + t) * K + lane + 32 * m] = v;
       }
       if (a.ca_out) {     // concept_alignment[t] = argmax_k cA[t][k] (first index on ties, :628); scale-invariant
         float bv = 0.0f;
         int bk = 0x7fffffff;
 #pragma unroll
         for (int m = 0; m < KC; ++m)
-          if (lane + 32 * m < K && (bk == 0x7fffffff || __float_as_uint(cs[m]) > __float_as_uint(bv))) { bv = cs[m]; bk = lane + 32 * m; }
+          if (cok[m] && (bk == 0x7fffffff || __float_as_uint(cs[m]) > __float_as_uint(bv))) { bv = cs[m]; bk = lane + 32 * m; }
         const int kbest = warp_argmax_nonneg32(bv, bk);
         if (lane == 0) a.ca_out[p0 + t] = kbest;
       }
