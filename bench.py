@@ -608,8 +608,8 @@ def gpu_arm(args):
         traffic = None
         try:                      # DRAM bytes of the dominant kernel per pair (ncu --set full), scaled to this launch
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
-            if tr.get('kernel') == dom and tr.get('variant') == args.variant and tr.get('n_concepts') == K_CONCEPTS:
-                traffic = tr['dram_bytes_per_pair'] * pk.n_pairs
+            if tr.get('variant') == args.variant and tr.get('n_concepts') == K_CONCEPTS and args.mixed == 'mixed':
+                traffic = tr['kernels'][dom]['dram_bytes_per_pair'] * pk.n_pairs
         except (OSError, ValueError, KeyError):
             pass
         gemm_flop = 2.0 * pk.n_regions * (D_FEAT + 1) * K_CONCEPTS
@@ -635,8 +635,9 @@ def gpu_arm(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None,
-            'dtype': 'f64' if not eng.mixed else 'f64 (concept chains, counts, statistics, softmax, M-step) + scaled f32 forward/'
-                     'backward lattice + split-tf32 tensor-core GEMMs with fp32 TMEM accumulation (precision %s)' % args.mixed,
+            'dtype': 'f64' if not eng.mixed else 'f64 (counts, statistics, softmax, M-step) + scaled f32 forward/backward lattice '
+                     '+ f32 concept chains (f32-pair clamped emission) + split-tf32 tensor-core GEMMs with fp32 TMEM accumulation '
+                     '(precision %s)' % args.mixed,
             'data': 'synthetic',
             'config': workload_config(args, args.pairs),
             'avg_log_likelihood': avg_ll,
@@ -874,9 +875,9 @@ def main():
     ap.add_argument('--model', default=None, choices=['linear', 'gaussian'],
                     help='image posterior: linear softmax or RBF (default: the config\'s)')
     ap.add_argument('--mixed', default='mixed',
-                    help="'mixed' (default: tcgen05 split-TF32 tensor-core GEMMs + scaled-float32 forward/backward lattice, "
-                         "validated at 1e-5 against float64 in the same run) | 'float64' (reference arithmetic everywhere) "
-                         "| 'all' (+ float32 concept chains) | subset like 'posterior+grad'")
+                    help="'mixed' (default: tcgen05 split-TF32 tensor-core GEMMs + scaled-float32 forward/backward lattice + "
+                         "float32 concept chains, validated at 1e-5 against float64 in the same run) | 'float64' (reference "
+                         "arithmetic everywhere) | subset like 'posterior+grad+recursion'")
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunks', type=int, default=0,

@@ -26,16 +26,16 @@ class MwdError(RuntimeError):
 def mixed_bits(spec):
     """modelConfigs['posterior_precision'] / engine ``mixed_precision`` -> MWD_MIXED_* bits.
     'float64' | None | 0: reference arithmetic everywhere (default).
-    'mixed': everything that holds the north-star tolerance (1e-5 on log-likelihood and every table over 20 EM
-             iterations, tests/test_gpu_mixed_precision.py) off the FP64 pipe: the two floor-free GEMMs (softmaxLayer,
-             updateSoftmaxWeight) on the tcgen05 tensor cores and the forward / backward lattice in scaled float32.
-    'all':   additionally the updateConceptCounts chains in float32 (measured 1.4e-5 on obs after 20 iterations).
+    'mixed' (= 'all'): everything that holds the north-star tolerance (1e-5 on log-likelihood and every table over
+             20 EM iterations, tests/test_gpu_mixed_precision.py) off the FP64 pipe: the two floor-free GEMMs
+             (softmaxLayer, updateSoftmaxWeight) on the tcgen05 tensor cores, the forward / backward lattice in scaled
+             float32, and the updateConceptCounts chains in float32 with the clamped emission carried as a float32
+             (hi, lo) pair (4.4e-6 on obs after 20 iterations; a single rounded float32 table gave 1.4e-5 and was
+             kept out of 'mixed' until the pair landed).
     Or an explicit int / '+'-joined subset of 'concept', 'posterior', 'grad', 'recursion'."""
     if spec is None or spec is False or spec == 0 or spec == 'float64':
         return 0
-    if spec is True or spec == 'mixed':
-        return MIXED_POSTERIOR | MIXED_GRAD | MIXED_RECURSION
-    if spec == 'all':
+    if spec is True or spec in ('mixed', 'all'):
         return MIXED_CONCEPT | MIXED_POSTERIOR | MIXED_GRAD | MIXED_RECURSION
     if isinstance(spec, int):
         return spec & 15

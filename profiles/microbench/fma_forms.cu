@@ -50,6 +50,47 @@ __global__ void k_ffma2(float* out, float a0, float b0) {
   for (int i = 0; i < NCH; ++i) { float2 v = *reinterpret_cast<float2*>(&acc[i]); s += v.x + v.y; }
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+__constant__ float2 c_f2[32];
+// packed FMA whose multiplier pair comes from __constant__ memory (compiler: FFMA2 R, R, UR, R)
+__global__ void k_ffma2_c(float* out) {
+  unsigned long long acc[NCH];
+  for (int i = 0; i < NCH; ++i) {
+    float2 v = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+    acc[i] = *reinterpret_cast<unsigned long long*>(&v);
+  }
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      float2 m = c_f2[i];
+      asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(*reinterpret_cast<unsigned long long*>(&m)), "l"(acc[(i + 1) % NCH]));
+    }
+  }
+  float s = 0;
+  for (int i = 0; i < NCH; ++i) { float2 v = *reinterpret_cast<float2*>(&acc[i]); s += v.x + v.y; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// packed FMA interleaved 1:1 with an integer ALU instruction: does FFMA2 leave issue slots free?
+__global__ void k_ffma2_mix(float* out, float a0, float b0, int q) {
+  unsigned long long acc[NCH], b[NCH], a;
+  int z[NCH];
+  for (int i = 0; i < NCH; ++i) {
+    float2 v = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i), w = make_float2(b0 + i * 1e-3f, b0 - i * 1e-3f);
+    acc[i] = *reinterpret_cast<unsigned long long*>(&v);
+    b[i] = *reinterpret_cast<unsigned long long*>(&w);
+    z[i] = threadIdx.x + i;
+  }
+  { float2 v = make_float2(a0, a0 * 0.999f); a = *reinterpret_cast<unsigned long long*>(&v); }
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(a), "l"(b[i]));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"(q), "r"(it));
+    }
+  }
+  float s = 0;
+  for (int i = 0; i < NCH; ++i) { float2 v = *reinterpret_cast<float2*>(&acc[i]); s += v.x + v.y + z[i]; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 __global__ void k_dfma(double* out, double a0, double b0) {
   double acc[NCH], b[NCH];
   for (int i = 0; i < NCH; ++i) { acc[i] = threadIdx.x * 1e-3 + i; b[i] = b0 + i * 1e-3; }
@@ -94,6 +135,11 @@ int main() {
   printf("ffma_c  %8.3f ms  %7.2f TFLOP/s  (%.1f FMA/clk/SM)\n", t, 2 * fmas / t / 1e9, fmas / (t * 1e-3) / sms / 1.965e9);
   t = time_ms([&] { k_ffma2<<<grid, block>>>((float*)buf, 0.9991f, 1e-3f); });
   printf("ffma2   %8.3f ms  %7.2f TFLOP/s  (%.1f FMA/clk/SM)\n", t, 4 * fmas / t / 1e9, 2 * fmas / (t * 1e-3) / sms / 1.965e9);
+  { float2 h2[32]; for (int i = 0; i < 32; ++i) h2[i] = make_float2(hf[i], hf[i]); cudaMemcpyToSymbol(c_f2, h2, sizeof(h2)); }
+  t = time_ms([&] { k_ffma2_c<<<grid, block>>>((float*)buf); });
+  printf("ffma2_c %8.3f ms  %7.2f TFLOP/s  (%.1f FMA/clk/SM)\n", t, 4 * fmas / t / 1e9, 2 * fmas / (t * 1e-3) / sms / 1.965e9);
+  t = time_ms([&] { k_ffma2_mix<<<grid, block>>>((float*)buf, 0.9991f, 1e-3f, 12345); });
+  printf("ffma2+lop3 1:1 %8.3f ms  %7.2f TFLOP/s  (%.1f FMA/clk/SM; the same number of FFMA2 as ffma2)\n", t, 4 * fmas / t / 1e9, 2 * fmas / (t * 1e-3) / sms / 1.965e9);
   t = time_ms([&] { k_dfma<<<grid, block>>>((double*)buf, 0.9991, 1e-3); });
   printf("dfma    %8.3f ms  %7.2f TFLOP/s  (%.1f FMA/clk/SM)\n", t, 2 * fmas / t / 1e9, fmas / (t * 1e-3) / sms / 1.965e9);
   t = time_ms([&] { k_dfma_c<<<grid, block>>>((double*)buf); });
