@@ -425,9 +425,10 @@ def gpu_arm(args):
                    mixed_precision=args.mixed)
     shard_bytes = sum(host[k].numel() * host[k].element_size() for k in host)
     if args.chunks <= 0:
-        # enough chunks to overlap the PCIe copy with the kernels, not so many that a small corpus
-        # drowns in launches (1 M pairs: 10.4 GB -> 16 chunks; MSCOCO-2k: 21 MB -> 1 chunk)
-        args.chunks = int(min(16, max(1, shard_bytes // (640 << 20))))
+        # enough chunks to overlap the PCIe copy with the kernels -- the kernels of the LAST chunk are the exposed
+        # tail -- not so many that a small corpus drowns in launches (1 M pairs on one GPU: 10.4 GB -> 32
+        # chunks; an eighth of it: 1.3 GB -> 10 chunks; MSCOCO-2k: 21 MB -> 1 chunk)
+        args.chunks = int(min(32, max(1, shard_bytes // (128 << 20))))
     in_l2 = shard_bytes * world < 2 * 126e6
     flush_buf = torch.empty((256 << 20,), dtype=torch.uint8, device=dev) if in_l2 else None
     use_graph = world == 1 and pk.n_pairs <= IKEngine.GRAPH_MAX_PAIRS and os.environ.get('MWD_GRAPH', '1') != '0'
@@ -582,6 +583,9 @@ def gpu_arm(args):
         tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
         dist.all_reduce(tot)
         h2d, d2h = int(tot[0]), int(tot[1])
+        per_rank = [None] * world              # where each rank's staging lives (diagnoses the host->device limiter)
+        dist.all_gather_object(per_rank, affinity)
+        affinity = per_rank
 
     # ---- align leg ("plus align-pairs/s separately"): batched Viterbi + cluster of the whole
     # shard under the current parameters (posterior GEMM + K6), alignments written to HBM
@@ -881,7 +885,7 @@ def main():
     ap.add_argument('--cpu-pairs', type=int, default=0, help='CPU-arm sample size (default 2048 x cores)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunks', type=int, default=0,
-                    help='chunks of the streamed (e2e) iteration (0 = one per ~640 MB of shard, at most 16)')
+                    help='chunks of the streamed (e2e) iteration (0 = one per ~128 MB of shard, at most 32)')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     for k, v in cfg.items():

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmwd_b200.so')
+# MWD_B200_LIB: an alternative build of the same library (A/B timing of a kernel change on one box)
+LIB_PATH = os.environ.get('MWD_B200_LIB') or os.path.join(_HERE, 'libmwd_b200.so')
 
 NMAX = 16
 KMAX = 128

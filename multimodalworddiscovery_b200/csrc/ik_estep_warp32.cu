@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
   const bool kv_last = on && (j + LPR * (KG - 1) < K);
 
   extern __shared__ float smem32[];
-  float* obsS = smem32;                                          // [P][K] scaled emission table
-  int* shS = reinterpret_cast<int*>(obsS + ((P * K + 3) & ~3));  // [P] shift of each phone type
+  float* obsS = smem32;                                          // [P][KS0] scaled emission table, columns >= K are 0
+  int* shS = reinterpret_cast<int*>(obsS + ((P * KS0 + 3) & ~3));   // [P] shift of each phone type
   float* buf = reinterpret_cast<float*>(shS + ((P + 3) & ~3)) + (size_t)wic * 2 * (N * KS);   // two gamma slices per warp
 
   // stage the emission table: row x scaled by 2^sh[x], sh = -(exponent of the row maximum) - 1 (max lands in [0.5,1))
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
     if (sh > 1000) sh = 1000;
     if (lane == 0) shS[x] = sh;
     const double sc = pow2d(sh);
-    for (int k = lane; k < K; k += 32) obsS[x * K + k] = (float)(a.obsT[(size_t)x * K + k] * sc);
+    for (int k = lane; k < KS0; k += 32) obsS[x * KS0 + k] = (k < K) ? (float)(a.obsT[(size_t)x * K + k] * sc) : 0.0f;
   }
   __syncthreads();
 
@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
   }
 
   auto load_obs = [&](float (&o)[KG], int x) {
-    const float* orow = obs_j + x * K;
+    const float* orow = obs_j + x * KS0;
 #pragma unroll
-    for (int q = 0; q < KG; ++q) o[q] = (q < KG - 1 || kv_last) ? orow[LPR * q] : 0.0f;
+    for (int q = 0; q < KG; ++q) o[q] = orow[LPR * q];      // padded rows: no guard on the last column group
   };
   auto warp_max = [&](const float (&v)[KG], float extra) {
     float m = extra;
@@ -328,11 +328,18 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       eb = ebo;
       // conceptCountsA[t][k] = sum_i gamma_t[i][k] / max(L, EPS);  phoneCounts[k][x_t] += ...  (:430,:233,:235)
       const double gsc = sg * inorm;
+      double cs64[KC];
 #pragma unroll
       for (int m = 0; m < KC; ++m) {
         const double v = (double)cs[m] * gsc;
         if (tab_on && cok[m]) __stcg(trow + 32 * m, tabv[m] + v);
-        if (a.cA_out && cok[m]) a.cA_out[(p0 + t) * K + lane + 32 * m] = v;
+        cs64[m] = v;
+      }
+      if (a.cA_out != nullptr) {      // materialised conceptCountsA (off by default): one uniform branch per step
+        double* crow = a.cA_out + (p0 + t) * K + lane;
+#pragma unroll
+        for (int m = 0; m < KC; ++m)
+          if (cok[m]) crow[32 * m] = cs64[m];
       }
       if (a.ca_out) {     // concept_alignment[t] = argmax_k cA[t][k] (first index on ties, :628); scale-invariant
         float bv = 0.0f;
@@ -415,7 +422,7 @@ static bool plan_warp32(int n, int K, int P, int Tmax, int64_t npairs, Warp32Pla
   if (!warp32_combo(n, pl->KG)) return false;
   const int ks0 = lpr * pl->KG;
   const int ks = ks0 + (((lpr - ks0) % 32) + 32) % 32;
-  pl->smem = ((size_t)((P * K + 3) & ~3) + ((P + 3) & ~3) + (size_t)kWpc32 * 2 * n * ks) * sizeof(float);
+  pl->smem = ((size_t)((P * ks0 + 3) & ~3) + ((P + 3) & ~3) + (size_t)kWpc32 * 2 * n * ks) * sizeof(float);
   const int cps = ctas32(pl->KG);
   if (pl->smem > (size_t)224 * 1024 / cps - 1024) return false;
   pl->NC = (Tmax + 1) / 2;
