@@ -26,6 +26,10 @@ namespace mwd {
 
 namespace {
 
+#ifndef MWD_W32_PF
+#define MWD_W32_PF 0      // checkpoint prefetch of the backward sweep: 0 off, 1 into L1, 2 into registers (measured at
+                          // 1 M MSCOCO pairs: 35.49 / 35.49 / 37.42 ms -- the L2 latency of the slice is already hidden)
+#endif
 constexpr int kWpc32 = 4;            // warps per CTA
 // CTAs per SM by lattice width: 16 warps at 128 registers up to 12 concepts per lane, 12 warps at 168 up to 17, else 8
 constexpr int ctas32(int KG) { return KG <= 12 ? 4 : (KG <= 17 ? 3 : 2); }
@@ -82,6 +86,9 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
   const bool on = lane < ROWL;
   const int i = on ? lane / LPR : 0;
   const int j = on ? lane - i * LPR : 0;
+  // (ptxas re-derives lane / LPR and the scratch / table base addresses inside the time loops, ~30 integer
+  // instructions per (pair, t) on the ncu source page; pinning them in registers with empty asm statements
+  // changed nothing, 35.4 -> 35.5 ms: the kernel is bound by its dependency chains, not by the issue count)
   const bool head = on && j == 0;
   const bool kv_last = on && (j + LPR * (KG - 1) < K);
 
@@ -268,6 +275,8 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       const double sg = pow2d(eg);
       double tabv[KC];
       double* trow = tab + x * K + lane;
+      // (unconditional loads from a clamped column instead of this guarded form: +6 ms, the loads then sit on the
+      // critical path of the step)
 #pragma unroll
       for (int m = 0; m < KC; ++m) tabv[m] = (tab_on && cok[m]) ? __ldcg(trow + 32 * m) : 0.0;
       float* grow = gslice + i * KS + j;
@@ -361,14 +370,40 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
     };
     const int nblk = (T + 1) / 2;
     int par = 0;
+#if MWD_W32_PF == 2
+    float a0n[KG];
+    {
+      const float* src = my_ckpt + (size_t)(nblk - 1) * SL;
+#pragma unroll
+      for (int q = 0; q < KG; ++q) a0n[q] = __ldcg(src + 32 * q);
+    }
+#endif
     for (int c = nblk - 1; c >= 0; --c) {
       const int t0 = 2 * c;
       float a0[KG];
+#if MWD_W32_PF == 2
+#pragma unroll
+      for (int q = 0; q < KG; ++q) a0[q] = a0n[q];
+      if (c > 0) {        // the next block's checkpoint travels while this block computes
+        const float* src = my_ckpt + (size_t)(c - 1) * SL;
+#pragma unroll
+        for (int q = 0; q < KG; ++q) a0n[q] = __ldcg(src + 32 * q);
+      }
+#else
       {
         const float* src = my_ckpt + (size_t)c * SL;
 #pragma unroll
-        for (int q = 0; q < KG; ++q) a0[q] = __ldcg(src + 32 * q);
+        for (int q = 0; q < KG; ++q) a0[q] = MWD_W32_PF ? __ldca(src + 32 * q) : __ldcg(src + 32 * q);
       }
+#if MWD_W32_PF == 1
+      if (c > 0) {        // pull the next block's checkpoint (one 128-byte line per register) from L2 into L1 meanwhile;
+                          // the lines were written by this very warp, so its own L1 cannot hold them stale
+        const float* nxt = my_ckpt + (size_t)(c - 1) * SL;
+#pragma unroll
+        for (int q = 0; q < KG; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + 32 * q));
+      }
+#endif
+#endif
       const int e0 = __ldcg(ck_exp + c);
       const int x0 = ph[t0];
       if (t0 + 1 < T) {
