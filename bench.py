@@ -54,6 +54,10 @@ def apply_variant(variant):
         K_CONCEPTS, P_PHONES, T_MEAN, T_STD = 100, 69, 49.0, 13.0
     else:
         K_CONCEPTS, P_PHONES, T_MEAN, T_STD = 65, 49, 50.0, 10.0
+    if os.environ.get('MWD_BENCH_CONCEPTS'):          # experiment knob: another concept count on the same corpus shape
+        K_CONCEPTS = int(os.environ['MWD_BENCH_CONCEPTS'])
+
+
 METRIC = 'em_caption_pairs_per_sec'
 UNIT = 'pairs/s'
 # BASELINE.json configs[0..4]

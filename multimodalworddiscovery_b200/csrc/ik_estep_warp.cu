@@ -74,7 +74,10 @@ __device__ __forceinline__ double row_sum_head(double v, int j) {
 // RB ("register block"): the checkpoint interval is fixed to 2 and the one recomputed alpha slice
 // stays in registers, so alpha never touches shared memory (only the gamma slice does, for the
 // column sums) and o_{t+1} is loaded once for the recompute and the backward step.
-template <int N, int KG, bool OBS_S, bool RB>
+// GEN ("generic width"): the instantiation is wider than the concept count needs (KG > ceil(K / LPR)), so ANY concept
+// group of a lane can lie beyond K, not just the last one; validity comes from per-lane bit masks.  Lets every
+// K <= LPR * KG run on the warp kernel instead of dropping to the CTA-per-4-pairs kernel (ik_estep.cu).
+template <int N, int KG, bool OBS_S, bool RB, bool GEN = false>
 __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp_kernel(const EstepArgs a) {
   constexpr int LPR = 32 / N;
   constexpr int ROWL = N * LPR;                                  // lanes that own lattice rows
@@ -94,6 +97,20 @@ __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp
   const int j = on ? lane - i * LPR : 0;
   const bool head = on && j == 0;
   const bool kv_last = on && (j + LPR * (KG - 1) < K);           // validity of the lane's last concept
+  unsigned ldmask = 0;                                           // GEN: bit q = column j + LPR q lies inside the table row
+  if constexpr (GEN) {
+#pragma unroll
+    for (int q = 0; q < KG; ++q) ldmask |= (j + LPR * q < K) ? (1u << q) : 0u;
+  }
+  const unsigned kvmask = on ? ldmask : 0u;                      // GEN: bit q = concept j + LPR q of this lane exists
+  auto kvalid = [&](int q) -> bool {
+    if constexpr (GEN) return (kvmask >> q) & 1u;
+    else return (q < KG - 1) ? on : kv_last;
+  };
+  auto ldvalid = [&](int q) -> bool {
+    if constexpr (GEN) return (ldmask >> q) & 1u;
+    else return q < KG - 1 || kv_last;
+  };
 
   extern __shared__ double smem[];
   const int obs_elems = OBS_S ? ((a.P * K + 1) & ~1) : 0;
@@ -122,7 +139,7 @@ __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp
     const double* orow = obs_j + x * K;
 #pragma unroll
     for (int q = 0; q < KG; ++q)
-      o[q] = (q < KG - 1 || kv_last) ? (OBS_S ? orow[LPR * q] : __ldg(orow + LPR * q)) : 0.0;
+      o[q] = ldvalid(q) ? (OBS_S ? orow[LPR * q] : __ldg(orow + LPR * q)) : 0.0;
   };
 
   for (int64_t pair = a.lo + gw; pair < a.hi; pair += total_warps) {
@@ -137,7 +154,7 @@ __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp
     {
       const double* prow = a.pz + (r0 + i) * K + j;
 #pragma unroll
-      for (int q = 0; q < KG; ++q) pz[q] = (q < KG - 1 ? on : kv_last) ? __ldcs(prow + LPR * q) : 0.0;
+      for (int q = 0; q < KG; ++q) pz[q] = kvalid(q) ? __ldcs(prow + LPR * q) : 0.0;
     }
 
     // ------------------------------------------------------------------ forward sweep
@@ -230,7 +247,7 @@ __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp
       double sumF = 0.0, dg = 0.0, rr = 0.0, sumF_b = 0.0, dg_b = 0.0, rr_b = 0.0;   // two chains each
 #pragma unroll
       for (int q = 0; q < KG; ++q) {
-        const bool kv = (q < KG - 1) ? on : kv_last;
+        const bool kv = kvalid(q);
         const double beta = fma(d_i, bo[q], w);
         const double g = av[q] * beta;
         const double f = kv ? floor_at(g, eps) : 0.0;
@@ -381,13 +398,15 @@ __global__ void __launch_bounds__(kWpc * 32, warp_ctas_per_sm(KG)) ik_estep_warp
 // ------------------------------------------------------------------------------------------
 struct WarpPlan {
   int KG, B, NC, grid, obs_s, rb;
+  bool gen;               // generic-width instantiation (KG wider than the concept count needs)
   size_t smem;
   int64_t warp_scratch;   // doubles per warp
 };
 
 // (n, KG) instantiations: K = 65 (MSCOCO, run_image2phone.py:43) and K = 50 / 100 (Flickr30k,
 // run_image2phone.py:73 / image_phone_hmm_word_discoverer.py:735) for the n they are fast for, plus K = 40 / 80.
-// Other concept counts run the generic CTA-per-4-pairs kernel (ik_estep.cu).
+// Other concept counts run a generic-width instantiation (MWD_WARP_GEN_COMBOS) where one is wide enough, else the
+// CTA-per-4-pairs kernel (ik_estep.cu).
 #define MWD_WARP_COMBOS(X)                                                              \
   X(1, 2) X(1, 3) X(1, 4) X(2, 4) X(2, 5) X(2, 7) X(3, 5) X(3, 7) X(3, 10) X(4, 7) X(4, 9) \
   X(4, 13) X(5, 9) X(5, 11) X(6, 10) X(6, 13)                                             \
@@ -400,6 +419,18 @@ struct WarpPlan {
 // n = 5 it measured 55.1 vs 60.3 ms at 1M pairs); MWD_ESTEPW_RB=0 selects the shared-memory block
 // variant instead
 #define MWD_WARP_RB_COMBOS(X) X(1, 3) X(2, 5) X(3, 7) X(4, 9) X(5, 11) X(6, 13) X(7, 17) X(8, 17)
+
+// generic-width instantiations (shared-memory-block variant): every exact width again with the per-group validity
+// mask, plus the widths that take n <= 4 up to K = 128; wider float64 lattices than these fall back to ik_estep.cu
+#define MWD_WARP_GEN_COMBOS(X) MWD_WARP_COMBOS(X) X(2, 8) X(3, 13) X(4, 16)
+
+static int warp_gen_width(int n, int KG) {
+  int best = 0;
+#define X(NN, GG) if (n == NN && GG >= KG && (best == 0 || GG < best)) best = GG;
+  MWD_WARP_GEN_COMBOS(X)
+#undef X
+  return best;
+}
 
 static int warp_kg(int n, int K) {
   const int lpr = 32 / n;
@@ -422,7 +453,12 @@ static bool plan_warp(int n, int K, int P, int Tmax, int64_t npairs, WarpPlan* p
   if (n < 1 || n > 10 || !warp_enabled()) return false;
   const int lpr = 32 / n;
   pl->KG = warp_kg(n, K);
-  if (!warp_combo(n, pl->KG)) return false;
+  pl->gen = false;
+  if (!warp_combo(n, pl->KG)) {
+    pl->KG = warp_gen_width(n, pl->KG);
+    if (pl->KG == 0) return false;
+    pl->gen = true;
+  }
   const int ks0 = lpr * pl->KG;
   const int ks = ks0 + (((lpr - ks0) % 16) + 16) % 16;
   const size_t slice = (size_t)kWpc * n * ks * sizeof(double);     // one alpha slice of every warp of a CTA
@@ -434,7 +470,7 @@ static bool plan_warp(int n, int K, int P, int Tmax, int64_t npairs, WarpPlan* p
   if (const char* e = getenv("MWD_ESTEPW_OBS")) pl->obs_s = (atoi(e) != 0 && obs_bytes + 2 * slice <= budget) ? 1 : 0;
   if (pl->obs_s) budget -= obs_bytes;
   pl->rb = 0;
-#define X(NN, GG) if (n == NN && pl->KG == GG) pl->rb = 1;
+#define X(NN, GG) if (n == NN && pl->KG == GG && !pl->gen) pl->rb = 1;
   MWD_WARP_RB_COMBOS(X)
 #undef X
   if (const char* e = getenv("MWD_ESTEPW_RB")) { if (atoi(e) == 0) pl->rb = 0; }
@@ -474,9 +510,9 @@ int64_t estep_warp_scratch(int n, int K, int P, int Tmax, int64_t npairs) {
   return pl.warp_scratch * pl.grid * kWpc;
 }
 
-template <int N, int KG, bool OBS_S, bool RB>
+template <int N, int KG, bool OBS_S, bool RB, bool GEN = false>
 static int launch_warp(const EstepArgs& a, const WarpPlan& pl, cudaStream_t st) {
-  auto kern = ik_estep_warp_kernel<N, KG, OBS_S, RB>;
+  auto kern = ik_estep_warp_kernel<N, KG, OBS_S, RB, GEN>;
   MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   kern<<<pl.grid, kWpc * 32, pl.smem, st>>>(a);
   MWD_CHECK_LAUNCH();
@@ -489,6 +525,15 @@ int estep_warp_launch(EstepArgs a, cudaStream_t st) {
   a.B = pl.B;
   a.NC = pl.NC;
   a.cta_scratch = pl.warp_scratch;
+  if (pl.gen) {
+#define X(NN, GG)                                                                     \
+  if (a.n == NN && pl.KG == GG)                                                       \
+    return pl.obs_s ? launch_warp<NN, GG, true, false, true>(a, pl, st) : launch_warp<NN, GG, false, false, true>(a, pl, st);
+    MWD_WARP_GEN_COMBOS(X)
+#undef X
+    set_error("warp E-step: no generic-width instantiation for (n=%d, KG=%d)", a.n, pl.KG);
+    return 2;
+  }
   if (pl.rb) {
 #define X(NN, GG)                                                                     \
   if (a.n == NN && pl.KG == GG)                                                       \

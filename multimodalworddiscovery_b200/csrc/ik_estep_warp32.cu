@@ -69,7 +69,10 @@ __device__ __forceinline__ int warp_argmax_nonneg32(float v, int k) {
   return __reduce_min_sync(0xffffffffu, b == mb ? k : 0x7fffffff);
 }
 
-template <int N, int KG>
+// GEN ("generic width"): the instantiation is wider than the concept count needs (KG > ceil(K / LPR)), so ANY concept
+// group of a lane can lie beyond K, not just the last one; validity comes from a per-lane bit mask.  Lets every
+// K <= LPR * KG run on the warp kernel instead of dropping to the CTA-per-4-pairs kernel (ik_estep.cu).
+template <int N, int KG, bool GEN = false>
 __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kernel(const EstepArgs a) {
   constexpr int LPR = 32 / N;
   constexpr int ROWL = N * LPR;
@@ -91,6 +94,15 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
   // changed nothing, 35.4 -> 35.5 ms: the kernel is bound by its dependency chains, not by the issue count)
   const bool head = on && j == 0;
   const bool kv_last = on && (j + LPR * (KG - 1) < K);
+  unsigned kvmask = 0;                                            // GEN: bit q = concept j + LPR q of this lane exists
+  if constexpr (GEN) {
+#pragma unroll
+    for (int q = 0; q < KG; ++q) kvmask |= (on && j + LPR * q < K) ? (1u << q) : 0u;
+  }
+  auto kvalid = [&](int q) -> bool {
+    if constexpr (GEN) return (kvmask >> q) & 1u;
+    else return (q < KG - 1) ? on : kv_last;
+  };
 
   extern __shared__ float smem32[];
   float* obsS = smem32;                                          // [P][KS0] scaled emission table, columns >= K are 0
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
     {
       const double* prow = a.pz + (r0 + i) * K + j;
 #pragma unroll
-      for (int q = 0; q < KG; ++q) pz[q] = (q < KG - 1 ? on : kv_last) ? (float)__ldcs(prow + LPR * q) : 0.0f;
+      for (int q = 0; q < KG; ++q) pz[q] = kvalid(q) ? (float)__ldcs(prow + LPR * q) : 0.0f;
     }
 
     // ------------------------------------------------------------------ forward sweep
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       float sumF = 0.0f, dg = 0.0f, rr = 0.0f, sumF_b = 0.0f, dg_b = 0.0f, rr_b = 0.0f;
 #pragma unroll
       for (int q = 0; q < KG; ++q) {
-        const bool kv = (q < KG - 1) ? on : kv_last;
+        const bool kv = kvalid(q);
         const float beta = fmaf(d_i, bo[q], w);
         const float g = av[q] * beta;
         const float f = kv ? fmaxf(g, epsf) : 0.0f;
@@ -430,6 +442,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
 
 struct Warp32Plan {
   int KG, NC, grid;
+  bool gen;               // generic-width instantiation (KG wider than the concept count needs)
   size_t smem;
   int64_t warp_scratch;   // doubles per warp
 };
@@ -442,11 +455,24 @@ struct Warp32Plan {
   X(7, 10) X(7, 13) X(7, 17) X(7, 20) X(7, 25) X(8, 10) X(8, 13) X(8, 17) X(8, 20) X(8, 25) X(9, 14) X(9, 17)     \
   X(9, 22) X(9, 27) X(10, 14) X(10, 17) X(10, 22) X(10, 27)
 
+// generic-width instantiations: every exact width again with the per-group validity mask, plus the widths that take
+// n <= 8 up to K = 128 (n = 9, 10: K <= 81 -- the state of a wider lattice does not fit the register file)
+#define MWD_WARP32_GEN_COMBOS(X) \
+  MWD_WARP32_COMBOS(X) X(2, 8) X(3, 13) X(4, 16) X(5, 22) X(6, 26) X(7, 32) X(8, 32)
+
 static bool warp32_combo(int n, int KG) {
 #define X(NN, GG) if (n == NN && KG == GG) return true;
   MWD_WARP32_COMBOS(X)
 #undef X
   return false;
+}
+// smallest generic-width instantiation of n that holds KG concept groups per lane; 0 if none
+static int warp32_gen_width(int n, int KG) {
+  int best = 0;
+#define X(NN, GG) if (n == NN && GG >= KG && (best == 0 || GG < best)) best = GG;
+  MWD_WARP32_GEN_COMBOS(X)
+#undef X
+  return best;
 }
 
 static bool plan_warp32(int n, int K, int P, int Tmax, int64_t npairs, Warp32Plan* pl) {
@@ -454,7 +480,12 @@ static bool plan_warp32(int n, int K, int P, int Tmax, int64_t npairs, Warp32Pla
   if (const char* e = getenv("MWD_ESTEP_WARP32")) { if (atoi(e) == 0) return false; }
   const int lpr = 32 / n;
   pl->KG = (K + lpr - 1) / lpr;
-  if (!warp32_combo(n, pl->KG)) return false;
+  pl->gen = false;
+  if (!warp32_combo(n, pl->KG)) {
+    pl->KG = warp32_gen_width(n, pl->KG);
+    if (pl->KG == 0) return false;
+    pl->gen = true;
+  }
   const int ks0 = lpr * pl->KG;
   const int ks = ks0 + (((lpr - ks0) % 32) + 32) % 32;
   pl->smem = ((size_t)((P * ks0 + 3) & ~3) + ((P + 3) & ~3) + (size_t)kWpc32 * 2 * n * ks) * sizeof(float);
@@ -473,9 +504,9 @@ static bool plan_warp32(int n, int K, int P, int Tmax, int64_t npairs, Warp32Pla
   return true;
 }
 
-template <int N, int KG>
+template <int N, int KG, bool GEN>
 static int launch_warp32(const EstepArgs& a, const Warp32Plan& pl, cudaStream_t st) {
-  auto kern = ik_estep_warp32_kernel<N, KG>;
+  auto kern = ik_estep_warp32_kernel<N, KG, GEN>;
   MWD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   kern<<<pl.grid, kWpc32 * 32, pl.smem, st>>>(a);
   MWD_CHECK_LAUNCH();
@@ -496,9 +527,15 @@ int estep_warp32_launch(EstepArgs a, cudaStream_t st) {
   a.B = 2;
   a.NC = pl.NC;
   a.cta_scratch = pl.warp_scratch;
-#define X(NN, GG) if (a.n == NN && pl.KG == GG) return launch_warp32<NN, GG>(a, pl, st);
-  MWD_WARP32_COMBOS(X)
+  if (!pl.gen) {
+#define X(NN, GG) if (a.n == NN && pl.KG == GG) return launch_warp32<NN, GG, false>(a, pl, st);
+    MWD_WARP32_COMBOS(X)
 #undef X
+  } else {
+#define X(NN, GG) if (a.n == NN && pl.KG == GG) return launch_warp32<NN, GG, true>(a, pl, st);
+    MWD_WARP32_GEN_COMBOS(X)
+#undef X
+  }
   set_error("float32 warp E-step: no instantiation for (n=%d, KG=%d)", a.n, pl.KG);
   return 2;
 }

@@ -85,6 +85,27 @@ def test_static_n_kernels_all_lengths():
     _run(f, x, 80, 9)
 
 
+@pytest.mark.parametrize('K,n_choices', [(33, list(range(1, 11))), (57, [2, 5, 7, 9]), (7, [1, 3, 6, 10]),
+                                         (128, [1, 4, 8]), (81, [9, 10]), (110, [3, 5, 6])])
+def test_generic_width_warp_kernels(K, n_choices):
+    """Concept counts without an exact (n, KG) instantiation run a WIDER warp kernel whose lanes mask the concept
+    groups beyond K (GEN template flag): same results as the oracle, no drop to the CTA-per-4-pairs kernel."""
+    rng = np.random.default_rng(K)
+    f, x = _corpus(rng, 30, n_choices, 2, 30, K=K, P=10, D=6)
+    _run(f, x, K, 10)
+
+
+def test_cta_kernel_forced(monkeypatch):
+    """MWD_ESTEP_WARP=0 keeps the CTA-per-4-pairs kernel (the fallback for n > 10 and very wide lattices) under the
+    same oracle comparison for shapes the warp kernels normally take."""
+    monkeypatch.setenv('MWD_ESTEP_WARP', '0')
+    rng = np.random.default_rng(11)
+    f, x = _corpus(rng, 30, list(range(1, 11)), 2, 25, K=65, P=11, D=6)
+    _run(f, x, 65, 11)
+    f, x = _corpus(rng, 20, [2, 5, 9], 2, 25, K=33, P=9, D=6)
+    _run(f, x, 33, 9, kind='gaussian')
+
+
 def test_large_phone_inventory_and_long_captions():
     rng = np.random.default_rng(4)
     f, x = _corpus(rng, 10, [2, 4], 20, 40, K=20, P=600, D=4)            # P*K*8 = 96 KB phone table

@@ -101,7 +101,9 @@ def test_recursion_float32_vs_float64_on_goldens(case):
 
 
 @pytest.mark.parametrize('K,n_choices,T_hi', [(65, [5], 125), (65, list(range(1, 11)), 125), (100, [1, 2, 3, 4, 5, 6, 7, 8], 125),
-                                             (40, [3, 9, 12], 60), (80, [2, 5, 10], 90), (50, [1, 4, 7], 125)])
+                                             (40, [3, 9, 12], 60), (80, [2, 5, 10], 90), (50, [1, 4, 7], 125),
+                                             # no exact instantiation: generic-width float32 kernels
+                                             (33, list(range(1, 11)), 60), (128, [2, 5, 8], 60), (81, [9, 10], 60), (7, [1, 6], 40)])
 def test_recursion_float32_full_shapes(K, n_choices, T_hi):
     rng = np.random.default_rng(K + len(n_choices))
     P, D = 49, 64
