@@ -662,6 +662,18 @@ struct Stage32 {
 };
 static Stage32 g_stage[16];
 
+// Which buckets take the float32 chains (MWD_MIXED_CONCEPT): measured per bucket at 1 M pairs (ncu launch lists of the
+// Flickr and coco10 shapes, profiles/r02_concept_per_bucket.txt) the float32 kernel wins from n = 4 on -- below that the
+// n x n products are too small to pay for its prologue / exponent bookkeeping (n = 3: 1.87 vs 1.44 ms) -- and loses
+// again for n >= 6 when the concept count leaves a 32-wide single-chain warp per region beside the paired ones
+// (K = 100: 2 n + 1 code variants per CTA; n = 8: 6.9 vs 2.8 ms).  MWD_CONCEPT32_MIN_N overrides the lower bound.
+static bool concept_bucket_f32(int n, int K) {
+  static const int min_n = getenv("MWD_CONCEPT32_MIN_N") ? atoi(getenv("MWD_CONCEPT32_MIN_N")) : 4;
+  if (n < min_n) return false;
+  const bool single_warps = n <= 8 && (K % 64) >= 32;
+  return !(single_warps && n >= 6);
+}
+
 static int concept_counts_f32(const mwd_ik_problem* p, cudaStream_t st, int dev) {
   const int K = p->n_concepts, P = p->n_phone_types;
   Stage32& sg = g_stage[dev];
@@ -706,7 +718,7 @@ static int concept_counts_f32(const mwd_ik_problem* p, cudaStream_t st, int dev)
     a.hi = p->bucket_lo[b + 1];
     a.K = K;
     a.Tmax = p->bucket_tmax[b];
-    if (a.hi <= a.lo) continue;
+    if (a.hi <= a.lo || !concept_bucket_f32(n, K)) continue;
     int rc;
     switch (n) {
 #define MWD_CASE(NN) case NN: rc = launch_concept32_auto<NN>(a, st); break;
@@ -723,7 +735,8 @@ static int concept_counts_f32(const mwd_ik_problem* p, cudaStream_t st, int dev)
   return 0;
 }
 
-static int concept_counts_f64(const mwd_ik_problem* p, cudaStream_t st) {
+// only_non_f32: run just the buckets the float32 path leaves to the float64 kernel
+static int concept_counts_f64(const mwd_ik_problem* p, cudaStream_t st, bool only_non_f32) {
   // the whole (tiny) parameter tables go to constant memory once per call, device-to-device
   MWD_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_trans, p->trans, sizeof(double) * (kNMax + 1) * kNMax * kNMax,
                                          0, cudaMemcpyDeviceToDevice, st));
@@ -742,7 +755,7 @@ static int concept_counts_f64(const mwd_ik_problem* p, cudaStream_t st) {
     a.hi = p->bucket_lo[b + 1];
     a.K = p->n_concepts;
     a.Tmax = p->bucket_tmax[b];
-    if (a.hi <= a.lo) continue;
+    if (a.hi <= a.lo || (only_non_f32 && concept_bucket_f32(n, p->n_concepts))) continue;
     int rc;
     switch (n) {
 #define MWD_CASE(NN) case NN: rc = launch_concept<NN>(a, st); break;
@@ -776,7 +789,15 @@ extern "C" int mwd_ik_concept_counts(const mwd_ik_problem* p, void* stream) {
   // per-frame emission tables of the image-audio classes (P = number of frames)
   const bool f32 = (p->mixed_precision & MWD_MIXED_CONCEPT) && p->part_phone != nullptr &&
                    (int64_t)p->n_phone_types * p->n_concepts <= (1 << 22);
-  int rc = f32 ? concept_counts_f32(p, st, dev) : concept_counts_f64(p, st);
+  bool any32 = false, any64 = !f32;
+  for (int b = 0; f32 && b < p->n_buckets; ++b) {
+    if (p->bucket_lo[b + 1] <= p->bucket_lo[b]) continue;
+    if (concept_bucket_f32(p->bucket_n[b], p->n_concepts)) any32 = true;
+    else any64 = true;
+  }
+  int rc = any32 ? concept_counts_f32(p, st, dev) : 0;
+  if (rc) return rc;
+  rc = any64 ? concept_counts_f64(p, st, f32) : 0;
   if (rc) return rc;
   if (!capturing) MWD_CHECK_CUDA(cudaEventRecord(g_const_event[dev], st));
   return 0;
