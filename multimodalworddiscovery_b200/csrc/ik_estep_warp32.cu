@@ -26,6 +26,11 @@ namespace mwd {
 
 namespace {
 
+#ifndef MWD_W32_KEEP
+#define MWD_W32_KEEP 1    // L2 evict_last policy on: bit 0 the checkpoint stores, bit 1 the phone-table updates.  Measured at
+                          // 1 M MSCOCO pairs (time / DRAM bytes per launch): 0: 35.58 ms / 50.3 GB, 1: 35.15 / 42.6,
+                          // 2: 35.23 / 43.2, 3: 35.19 / 42.2 -- the streamed row statistics and posteriors leave L2 first
+#endif
 #ifndef MWD_W32_PF
 #define MWD_W32_PF 0      // checkpoint prefetch of the backward sweep: 0 off, 1 into L1, 2 into registers (measured at
                           // 1 M MSCOCO pairs: 35.49 / 35.49 / 37.42 ms -- the L2 latency of the slice is already hidden)
@@ -53,6 +58,18 @@ __device__ __forceinline__ float row_sum_head32(float v, int j) {
     for (int off = P2 / 2; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
     return v;
   }
+}
+
+__device__ __forceinline__ uint64_t l2_keep_policy32() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_keep32(float* p, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep64(double* p, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 
 // 2^e as a double / float.  pow2d clamps below at 2^-1022: raw values under that are 0 or denormal in the reference too
@@ -146,6 +163,7 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
   double* tab = a.part_phone + (size_t)gw * P * K;
   const float* obs_j = obsS + j;
 
+  const uint64_t keep = (MWD_W32_KEEP != 0) ? l2_keep_policy32() : 0;
   int ccol[KC];
   bool cok[KC];
 #pragma unroll
@@ -219,7 +237,10 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
         if (!a.ll_only && (t & 1) == 0) {
           float* dst = my_ckpt + (size_t)cidx * SL;
 #pragma unroll
-          for (int q = 0; q < KG; ++q) __stcg(dst + 32 * q, al[q]);
+          for (int q = 0; q < KG; ++q) {
+            if (MWD_W32_KEEP & 1) st_keep32(dst + 32 * q, al[q], keep);
+            else __stcg(dst + 32 * q, al[q]);
+          }
           if (lane == 0) __stcg(ck_exp + cidx, ea);
           ++cidx;
         }
@@ -353,7 +374,10 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
 #pragma unroll
       for (int m = 0; m < KC; ++m) {
         const double v = (double)cs[m] * gsc;
-        if (tab_on && cok[m]) __stcg(trow + 32 * m, tabv[m] + v);
+        if (tab_on && cok[m]) {
+          if (MWD_W32_KEEP & 2) st_keep64(trow + 32 * m, tabv[m] + v, keep);
+          else __stcg(trow + 32 * m, tabv[m] + v);
+        }
         cs64[m] = v;
       }
       if (a.cA_out != nullptr) {      // materialised conceptCountsA (off by default): one uniform branch per step
