@@ -29,6 +29,10 @@
 #include <stdlib.h>
 
 #include <mutex>
+
+#ifndef MWD_C32_PROLOGUE_F32
+#define MWD_C32_PROLOGUE_F32 1      // float32 phone-table prologue of the float32 chains (0: float64)
+#endif
 #include <type_traits>
 
 #include "mwd_common.cuh"
@@ -207,6 +211,7 @@ struct ConceptArgs32 {
                             // obsT[x][k] * 2^shift[x]; one 128-bit load serves the two chains of a paired lane
   const int32_t* shift;     // (P)
   const double* obsKP;      // (K x P) float64, column x scaled by 2^shift[x] (phone-table form of the marginal emissions)
+  const float* obsKPf;      // the same table rounded to float32 (float32 prologue)
   int P, kseg_n;            // phone inventory; k-segments of the phone-table prologue (0: direct per-(t, j) dot products)
   const float* trans32;     // float32 copies of the full tables in GLOBAL memory (register-resident path)
   const float* init32;
@@ -218,7 +223,7 @@ struct ConceptArgs32 {
 // obsS[x][k] = obsT[x][k] * 2^shift[x], shift[x] = -ceil(log2(max_k obsT[x][k])) (0 for an all-zero row);
 // one warp per phone type.  Also converts the transition / initial tables to float32.
 __global__ void concept_prepare32_kernel(const double* __restrict__ obsT, int P, int K, float4* __restrict__ obsS,
-                                         double* __restrict__ obsKP,
+                                         double* __restrict__ obsKP, float* __restrict__ obsKPf,
                                          int32_t* __restrict__ shift, const double* __restrict__ trans,
                                          const double* __restrict__ init, float* __restrict__ trans32,
                                          float* __restrict__ init32) {
@@ -247,7 +252,10 @@ __global__ void concept_prepare32_kernel(const double* __restrict__ obsT, int P,
       const float hi = (float)v;
       row[(k >> 1) * 4 + (k & 1)] = hi;
       row[(k >> 1) * 4 + (k & 1) + 2] = (float)(v - (double)hi);
-      if (k < K) obsKP[(size_t)k * P + x] = v;
+      if (k < K) {
+        obsKP[(size_t)k * P + x] = v;
+        obsKPf[(size_t)k * P + x] = hi;
+      }
     }
   }
 }
@@ -291,7 +299,14 @@ __global__ void __launch_bounds__(1024) ik_concept32_kernel(const ConceptArgs32 
   int* s_exp = reinterpret_cast<int*>(s_off + PPC * Tmax);          // [PPC][N][K] chain exponents
   double* s_part = reinterpret_cast<double*>(s_exp + PPC * NK + ((PPC * (Tmax + NK)) & 1));   // [PPC][S][P][N] (8-byte aligned)
 
-  for (int e = tid; e < npair * NK; e += blockDim.x) s_pz[e] = a.pz[r0 * K + e];
+  // float32 copy of the posteriors for the float32 prologue; it borrows s_num, which is first written when the chains
+  // publish their results
+  float* s_pzf = reinterpret_cast<float*>(s_num);
+  for (int e = tid; e < npair * NK; e += blockDim.x) {
+    const double v = a.pz[r0 * K + e];
+    s_pz[e] = v;
+    if (MWD_C32_PROLOGUE_F32) s_pzf[e] = (float)v;
+  }
   for (int q = 0; q < npair; ++q) {
     const int p0 = a.phone_off[pair0 + q], T = a.phone_off[pair0 + q + 1] - p0;
     for (int t = tid; t < T; t += blockDim.x)
@@ -306,21 +321,39 @@ __global__ void __launch_bounds__(1024) ik_concept32_kernel(const ConceptArgs32 
   // at P = 49, T = 50 (ncu: 47 % of the warps' resident time was spent before the chains started).
   if (a.kseg_n > 0) {
     const int P = a.P, S = a.kseg_n, kseg = (K + S - 1) / S;
+    float* s_partf = reinterpret_cast<float*>(s_part);
     for (int item = tid; item < npair * S * P; item += blockDim.x) {
       const int q = item / (S * P), r = item - q * (S * P), seg = r / P, x = r - seg * P;
-      const double* pzq = s_pz + q * NK;
       const int k1 = min(K, (seg + 1) * kseg);
-      double acc[N];
+      if (MWD_C32_PROLOGUE_F32) {
+        // float32 phone table: the marginal emissions are rounded to float32 below anyway, and their rounding differs
+        // from pair to pair (it averages out over the corpus, profiles/r02_mixed_precision.md section 5)
+        const float* pzq = s_pzf + q * NK;
+        float acc[N];
 #pragma unroll
-      for (int j = 0; j < N; ++j) acc[j] = 0.0;
-      for (int k = seg * kseg; k < k1; ++k) {
-        const double o = __ldg(a.obsKP + (size_t)k * P + x);
+        for (int j = 0; j < N; ++j) acc[j] = 0.0f;
+        for (int k = seg * kseg; k < k1; ++k) {
+          const float o = __ldg(a.obsKPf + (size_t)k * P + x);
 #pragma unroll
-        for (int j = 0; j < N; ++j) acc[j] = fma(pzq[j * K + k], o, acc[j]);
+          for (int j = 0; j < N; ++j) acc[j] = fmaf(pzq[j * K + k], o, acc[j]);
+        }
+        float* dst = s_partf + ((size_t)(q * S + seg) * P + x) * N;
+#pragma unroll
+        for (int j = 0; j < N; ++j) dst[j] = acc[j];
+      } else {
+        const double* pzq = s_pz + q * NK;
+        double acc[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[j] = 0.0;
+        for (int k = seg * kseg; k < k1; ++k) {
+          const double o = __ldg(a.obsKP + (size_t)k * P + x);
+#pragma unroll
+          for (int j = 0; j < N; ++j) acc[j] = fma(pzq[j * K + k], o, acc[j]);
+        }
+        double* dst = s_part + ((size_t)(q * S + seg) * P + x) * N;
+#pragma unroll
+        for (int j = 0; j < N; ++j) dst[j] = acc[j];
       }
-      double* dst = s_part + ((size_t)(q * S + seg) * P + x) * N;
-#pragma unroll
-      for (int j = 0; j < N; ++j) dst[j] = acc[j];
     }
     __syncthreads();
     for (int q = 0; q < npair; ++q) {
@@ -328,9 +361,15 @@ __global__ void __launch_bounds__(1024) ik_concept32_kernel(const ConceptArgs32 
       for (int e = tid; e < T * N; e += blockDim.x) {
         const int t = e / N, j = e - t * N;
         const int x = a.phones[p0 + t];
-        double v = 0.0;
-        for (int seg = 0; seg < S; ++seg) v += s_part[((size_t)(q * S + seg) * P + x) * N + j];
-        s_e[((size_t)q * Tmax + t) * NP + j] = (float)v;
+        if (MWD_C32_PROLOGUE_F32) {
+          float v = 0.0f;
+          for (int seg = 0; seg < S; ++seg) v += s_partf[((size_t)(q * S + seg) * P + x) * N + j];
+          s_e[((size_t)q * Tmax + t) * NP + j] = v;
+        } else {
+          double v = 0.0;
+          for (int seg = 0; seg < S; ++seg) v += s_part[((size_t)(q * S + seg) * P + x) * N + j];
+          s_e[((size_t)q * Tmax + t) * NP + j] = (float)v;
+        }
       }
     }
   } else {
@@ -684,7 +723,7 @@ static int concept_counts_f32(const mwd_ik_problem* p, cudaStream_t st, int dev)
     if (sg.obsS) { cudaFree(sg.obsS); cudaFree(sg.shift); cudaFree(sg.obsKP); }
     MWD_CHECK_CUDA(cudaMalloc(&sg.obsS, (size_t)P * ((K + 1) / 2) * sizeof(float4)));
     MWD_CHECK_CUDA(cudaMalloc(&sg.shift, (size_t)P * sizeof(int32_t)));
-    MWD_CHECK_CUDA(cudaMalloc(&sg.obsKP, need * sizeof(double)));
+    MWD_CHECK_CUDA(cudaMalloc(&sg.obsKP, need * (sizeof(double) + sizeof(float))));   // float64 table, then its float32 copy
     sg.cap = need;
   }
   if (!sg.trans32) {
@@ -692,7 +731,8 @@ static int concept_counts_f32(const mwd_ik_problem* p, cudaStream_t st, int dev)
     MWD_CHECK_CUDA(cudaMalloc(&sg.init32, sizeof(float) * (kNMax + 1) * kNMax));
   }
   concept_prepare32_kernel<<<(P * 32 + 255) / 256 < 8 ? 8 : (P * 32 + 255) / 256, 256, 0, st>>>(
-      p->obsT, P, K, sg.obsS, sg.obsKP, sg.shift, p->trans, p->init, sg.trans32, sg.init32);
+      p->obsT, P, K, sg.obsS, sg.obsKP, reinterpret_cast<float*>(sg.obsKP + sg.cap), sg.shift, p->trans, p->init,
+      sg.trans32, sg.init32);
   MWD_CHECK_LAUNCH();
   MWD_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_trans32, sg.trans32, sizeof(float) * (kNMax + 1) * kNMax * kNMax, 0,
                                          cudaMemcpyDeviceToDevice, st));
@@ -709,6 +749,7 @@ static int concept_counts_f32(const mwd_ik_problem* p, cudaStream_t st, int dev)
     a.obsS = sg.obsS;
     a.shift = sg.shift;
     a.obsKP = sg.obsKP;
+    a.obsKPf = reinterpret_cast<const float*>(sg.obsKP + sg.cap);
     a.P = P;
     a.kseg_n = 0;
     a.trans32 = sg.trans32;
