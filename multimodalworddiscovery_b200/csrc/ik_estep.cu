@@ -405,6 +405,35 @@ struct CountsArgs {
   int64_t lo, hi;
   int n, total_warps;
   double eps;            // xi floor (MWD_EPS or 0)
+  int compact;           // rows written by the float32 kernel: see StatRow
+  int K;                 // concept count (compact rows of an all-floored step stand for K * eps)
+};
+
+// One (pair, t) row of the statistics the E-step kernels hand to the count post-pass.  Float64 kernels: 4 n doubles
+// [s | F | dg | r].  The float32 kernel (ik_estep_warp32.cu) writes the SAME slot compactly -- 4 n float32 mantissas,
+// then the binary exponents of s, of (F, dg) and of r, then a flag "every entry of the step was floored" (F = K eps)
+// -- 16 n + 16 bytes instead of 32 n, rows packed densely from the start of the bucket's slot range: the un-scaling
+// (double)m * 2^e  it used to do before the store happens here, with identical results.
+struct StatRow {
+  const double* row;
+  double es, ef, er;     // 2^e factors (1 for float64 rows)
+  bool compact, floored;
+  __device__ __forceinline__ StatRow(const double* r, bool c) : row(r), es(1.0), ef(1.0), er(1.0), compact(c), floored(false) {}
+  // row g (counted from the bucket's first row) of a bucket whose statistics start at `base`
+  __device__ __forceinline__ static const double* at(const double* base, int64_t g, int n, bool c) {
+    return c ? reinterpret_cast<const double*>(reinterpret_cast<const float*>(base) + g * (4 * n + 4)) : base + g * 4 * n;
+  }
+  __device__ __forceinline__ const double* next(int n) const { return at(row, 1, n, compact); }
+  __device__ __forceinline__ static double p2(int e) { return __longlong_as_double((long long)(max(e, -1022) + 1023) << 52); }
+  __device__ __forceinline__ void load_exps(int n) {
+    if (compact) {
+      const int4 e = __ldcs(reinterpret_cast<const int4*>(reinterpret_cast<const float*>(row) + 4 * n));
+      es = p2(e.x); ef = p2(e.y); er = p2(e.z); floored = e.w != 0;
+    }
+  }
+  __device__ __forceinline__ double raw(int idx) const {
+    return compact ? (double)__ldcs(reinterpret_cast<const float*>(row) + idx) : __ldcs(row + idx);
+  }
 };
 
 __device__ __forceinline__ double warp_sum_all(double v) {
@@ -439,22 +468,27 @@ __global__ void __launch_bounds__(256) ik_counts_kernel(const CountsArgs a) {
   double acc_i = 0.0;
   for (int64_t pair = a.lo + gw; pair < a.hi; pair += a.total_warps) {
     const int T = a.phone_off[pair + 1] - a.phone_off[pair];
-    const double* st = a.stats + 4 * a.slot_off[pair];
+    const int64_t s_lo = a.slot_off[a.lo];
+    const double* base = a.stats + 4 * s_lo;
+    const int64_t g0 = (a.slot_off[pair] - s_lo) / n;      // the pair's first row, counted from the bucket's first
     for (int t = 0; t < T; ++t) {
-      const double* row = st + (size_t)t * 4 * n;
+      StatRow row(StatRow::at(base, g0 + t, n, a.compact != 0), a.compact != 0);
+      row.load_exps(n);
       // updateInitialCounts: sum_k max(g,EPS) per region over its total (:355)
-      const double f = (lane < n) ? __ldcg(row + n + lane) : 0.0;
+      const double f = (lane < n) ? (row.floored ? (double)a.K * a.eps : row.raw(n + lane) * row.ef) : 0.0;
       double xv[EPL];
       double z = 0.0;
       if (t < T - 1) {
         // xi_t = diag(d o beta alpha) + s_t Aoff r_{t+1}, EPS-floored, normalised (:388-396)
-        const double* nxt = row + 4 * n;
+        StatRow nxt(row.next(n), a.compact != 0);
+        nxt.load_exps(n);
 #pragma unroll
         for (int q = 0; q < EPL; ++q) {
           xv[q] = 0.0;
           if (q < epl && lane + 32 * q < nn) {
-            const double u = __ldcg(row + off_a[q]);
-            const double xi = (coef[q] < 0.0) ? u : (u * coef[q]) * __ldcg(nxt + off_b[q]);
+            // off_a is a slot of s (< n) for an off-diagonal entry, of dg for a diagonal one; off_b a slot of r
+            const double u = row.raw(off_a[q]) * ((coef[q] < 0.0) ? row.ef : row.es);
+            const double xi = (coef[q] < 0.0) ? u : (u * coef[q]) * (nxt.raw(off_b[q]) * nxt.er);
             xv[q] = floor_at(xi, a.eps);
             z += xv[q];
           }
@@ -518,23 +552,52 @@ __global__ void __launch_bounds__(256) ik_counts_small_kernel(const CountsArgs a
   const int64_t g_end = min(rows, (int64_t)(gw + 1) * chunk);
   for (int64_t g = (int64_t)gw * chunk + lane; g < g_end; g += 32) {
     {
-      const double* row = base + (size_t)g * 4 * N;
-      double f[N], Ft = 0.0;
+      double f[N], sv[N], dgv[N], rn[N], Ft = 0.0;
+      bool has_next;
+      if (a.compact) {
+        // the lane's whole row (4 N mantissas, 3 exponents, flag) in N + 1 128-bit loads; of the next row only r and its exponent
+        const float* rp = reinterpret_cast<const float*>(base) + g * (4 * N + 4);
+        float rw[4 * N + 4];
 #pragma unroll
-      for (int r = 0; r < N; ++r) { f[r] = __ldcs(row + N + r); Ft += f[r]; }
+        for (int q = 0; q < N + 1; ++q) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(rp) + q);
+          rw[4 * q] = v.x; rw[4 * q + 1] = v.y; rw[4 * q + 2] = v.z; rw[4 * q + 3] = v.w;
+        }
+        const double es = StatRow::p2(__float_as_int(rw[4 * N])), ef = StatRow::p2(__float_as_int(rw[4 * N + 1]));
+        const bool floored = __float_as_int(rw[4 * N + 3]) != 0;
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+          sv[r] = (double)rw[r] * es;
+          f[r] = floored ? (double)a.K * eps : (double)rw[N + r] * ef;
+          dgv[r] = (double)rw[2 * N + r] * ef;
+        }
+        has_next = !(sv[0] < 0.0) && g + 1 < rows;
+        if (has_next) {
+          const float* nx = rp + (4 * N + 4);
+          const double er = StatRow::p2(__float_as_int(__ldcs(nx + 4 * N + 2)));
+#pragma unroll
+          for (int r = 0; r < N; ++r) rn[r] = (double)__ldcs(nx + 3 * N + r) * er;
+        }
+      } else {
+        const double* row = base + (size_t)g * 4 * N;
+#pragma unroll
+        for (int r = 0; r < N; ++r) { f[r] = __ldcs(row + N + r); sv[r] = __ldcs(row + r); }
+        has_next = !(sv[0] < 0.0) && g + 1 < rows;
+        if (has_next) {
+#pragma unroll
+          for (int r = 0; r < N; ++r) {
+            dgv[r] = __ldcs(row + 2 * N + r);
+            rn[r] = __ldcs(row + 4 * N + 3 * N + r);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < N; ++r) Ft += f[r];
       const double iF = 1.0 / Ft;
 #pragma unroll
       for (int r = 0; r < N; ++r) acc_i[r] = fma(f[r], iF, acc_i[r]);                 // :355
-      double sv[N];
-#pragma unroll
-      for (int r = 0; r < N; ++r) sv[r] = __ldcs(row + r);
-      if (!(sv[0] < 0.0) && g + 1 < rows) {
-        double dgv[N], rn[N], xv[N * N], z = 0.0;
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-          dgv[r] = __ldcs(row + 2 * N + r);
-          rn[r] = __ldcs(row + 4 * N + 3 * N + r);
-        }
+      if (has_next) {
+        double xv[N * N], z = 0.0;
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
@@ -787,6 +850,8 @@ static int estep_impl(const mwd_ik_problem* p, void* stream, int ll_only) {
       c.hi = hi;
       c.n = n;
       c.eps = a.eps;
+      c.compact = use_warp32 ? 1 : 0;
+      c.K = p->n_concepts;
       c.total_warps = estep_grid_rows() * 8;     // one partial row per CTA, 8 warps per CTA
       switch (n) {
         case 1: ik_counts_small_kernel<1><<<estep_grid_rows(), 256, 0, st>>>(c); break;

@@ -9,8 +9,9 @@
 //     max(alpha beta, EPS) = 2^(ea+eb) * max(a^ b^, EPS * 2^-(ea+eb))
 // and if EPS * 2^-(ea+eb) is beyond float32 every entry is floored, the floored row sum is exactly K * EPS.
 // The lattice values (32 x KG per step) are float32 in [2^-126, ~1] after power-of-two renormalisation (exact);
-// everything that leaves the warp is float64 again: the per-step row statistics handed to the count post-pass are
-// un-scaled in float64 (so ik_counts_*_kernel, which applies the xi / init floors, is unchanged), the phone table
+// everything that leaves the warp is float64 again: the per-step row statistics handed to the count post-pass travel
+// as float32 mantissas + the step's exponents and are un-scaled to float64 by the reader (StatRow in ik_estep.cu; the
+// xi / init floors are applied there on raw float64 values as before -- 92 instead of 160 bytes per step), the phone table
 // accumulates  float64(sum_i gamma^) * 2^(ea+eb) / max(L, EPS)  in float64, log-likelihood in float64.
 // The emission table is staged in shared memory as float32 with one power-of-two shift per phone type.
 //
@@ -190,7 +191,13 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
     const int T = a.phone_off[pair + 1] - (int32_t)p0;
     const int64_t r0 = a.region_off[pair];
     const int32_t* ph = a.phones + p0;
-    double* st = a.stats + 4 * a.slot_off[pair] + i;
+    // row t of the pair's statistics: 4 n float32 mantissas [s | F | dg | r], the exponents of s, (F, dg), r and the
+    // all-floored flag (StatRow in ik_estep.cu un-scales them).  Rows of 4 n + 4 words are packed densely from the
+    // start of the bucket's slot range (they need 16 n + 16 of the 32 n bytes a float64 row has), in global row order
+    constexpr int RS = 4 * N + 4;             // row stride in 32-bit words
+    const int64_t s_lo = a.slot_off[a.lo];
+    float* st = reinterpret_cast<float*>(a.stats + 4 * s_lo) + ((a.slot_off[pair] - s_lo) / N) * RS + i;
+    int* st_e = reinterpret_cast<int*>(st - i) + 4 * N;
     if (T <= 0) continue;
 
     float pz[KG];
@@ -261,7 +268,8 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
           double L = unscale(Lh, ea);
           L = floor_at(L, eps);
           if (lane == 0) a.pair_ll[pair] = log(L);                       // :529
-          if (head && !a.ll_only) __stcs(st + (t * 4 + 0) * N, -1.0);    // sentinel: last row of the pair
+          if (head && !a.ll_only) __stcs(st + t * RS, -1.0f);            // sentinel: last row of the pair
+          if (lane == 0 && !a.ll_only) __stcs(st_e + t * RS, 0);
           inorm = 1.0 / L;
         } else {
           float c = 0.0f;
@@ -269,8 +277,9 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
           for (int jp = 0; jp < N; ++jp) c = fmaf(acol[jp], sv[jp], c);
           if (head && !a.ll_only) {
             __stcg(hist + t * N, c);
-            __stcs(st + (t * 4 + 0) * N, unscale(s, ea));
+            __stcs(st + t * RS, s);
           }
+          if (lane == 0 && !a.ll_only) __stcs(st_e + t * RS, ea);
 #pragma unroll
           for (int q = 0; q < KG; ++q) al[q] = onext[q] * fmaf(d_i, al[q], c * pz[q]);
           ea -= shn;
@@ -351,16 +360,16 @@ __global__ void __launch_bounds__(kWpc32 * 32, ctas32(KG)) ik_estep_warp32_kerne
       sumF = row_sum_head32<LPR>(sumF, j);
       dg = row_sum_head32<LPR>(dg, j);
       rr = row_sum_head32<LPR>(rr, j);
-      {                   // row statistics of this step for the count post-pass, un-scaled float64 (head lanes store)
-        // every entry floored: the K concepts of the row contribute EPS each
-        const double v1 = all_floored ? (double)K * eps : (double)sumF * sg;
-        const double v2 = (double)dg * sg;
-        const double v3 = unscale(rr, ebo);
-        double* sp = st + (t * 4 + 1) * N;
+      {                   // row statistics of this step for the count post-pass (head lanes store)
+        float* sp = st + t * RS;
         if (head) {
-          __stcs(sp, v1);
-          __stcs(sp + N, v2);
-          __stcs(sp + 2 * N, v3);
+          __stcs(sp + N, sumF);
+          __stcs(sp + 2 * N, dg);
+          __stcs(sp + 3 * N, rr);
+        }
+        if (lane == 0) {    // exponents of (F, dg) and of r; flag: every entry floored, the K concepts of a row give EPS each
+          __stcs(st_e + t * RS + 1, eg);
+          __stcs(reinterpret_cast<int2*>(st_e + t * RS + 2), make_int2(ebo, all_floored ? 1 : 0));
         }
       }
       float wn = 0.0f;
