@@ -173,3 +173,34 @@ def test_radix_digit_argsort_matches_numpy_stable():
         keys = rng.integers(0, bound, 50000).astype(np.int64)
         assert np.array_equal(_stable_argsort_u16_digits(keys, bound), np.argsort(keys, kind='stable'))
     assert _stable_argsort_u16_digits(np.zeros(0, np.int64), 5).shape == (0,)
+
+
+def test_mixed_precision_spec_parsing():
+    """modelConfigs['posterior_precision'] -> MWD_MIXED_* bits: 'mixed' is everything that passes the 1e-5 gate
+    ('all' is kept as a synonym), subsets are '+'-joined, the default is the reference arithmetic."""
+    every = _lib.MIXED_CONCEPT | _lib.MIXED_POSTERIOR | _lib.MIXED_GRAD | _lib.MIXED_RECURSION
+    for spec in (None, False, 0, 'float64'):
+        assert _lib.mixed_bits(spec) == 0
+    assert _lib.mixed_bits('mixed') == _lib.mixed_bits('all') == _lib.mixed_bits(True) == every
+    assert _lib.mixed_bits('posterior+grad') == _lib.MIXED_POSTERIOR | _lib.MIXED_GRAD
+    assert _lib.mixed_bits('recursion + concept') == _lib.MIXED_RECURSION | _lib.MIXED_CONCEPT
+    assert _lib.mixed_bits(every | 64) == every
+    with pytest.raises(KeyError):
+        _lib.mixed_bits('tensor')
+
+
+def test_library_path_override(tmp_path):
+    """MWD_B200_LIB names another build of the library (A/B timing); a wrong path fails loudly, there is no fallback."""
+    import subprocess
+    import sys
+    bogus = str(tmp_path / 'libmwd_other.so')
+    code = ('from multimodalworddiscovery_b200 import _lib\n'
+            'assert _lib.LIB_PATH == %r, _lib.LIB_PATH\n'
+            'try:\n'
+            '    _lib.load()\n'
+            'except _lib.MwdError as e:\n'
+            '    print("LOUD", e)\n' % bogus)
+    env = dict(os.environ, MWD_B200_LIB=bogus, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert 'LOUD' in out.stdout and 'no CPU fallback' in out.stdout
