@@ -309,11 +309,14 @@ class IKEngine(object):
         # posterior (RBF: + expansion kernel) | per bucket: recursion + count post-pass + concept chains |
         # reduce_counts: 3 tables x 2 levels + 2 log-likelihood stages | gradient GEMM + its reduction |
         # M-step: init/trans, obs, posterior parameter
-        post = 2 if self.gaussian else 1
+        # mixed path: + the weight-split kernel of the tensor-core posterior, + the table-preparation kernel of the
+        # float32 concept chains (one per call)
+        post = (2 if self.gaussian else 1) + (1 if self._tc_posterior else 0)
+        prep = 1 if (self.mixed & _lib.MIXED_CONCEPT) else 0
         if n_chunks is None:
             nb = int(np.count_nonzero(np.diff(self._bucket_lo) > 0))
-            return post + 3 * nb + 8 + 2 + 3
-        per_chunk = sum(post + 3 * len(ch['bucket_n']) + 1 for ch in self.plan_chunks(n_chunks))
+            return post + 3 * nb + prep + 8 + 2 + 3
+        per_chunk = sum(post + 3 * len(ch['bucket_n']) + prep + 1 for ch in self.plan_chunks(n_chunks))
         return per_chunk + 8 + 1 + 3
 
     # ------------------------------------------------------------------ parameter snapshots (device to device)
